@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — allocation decisions/sec of the best-fit path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl native|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic requests: score R
+requests against the node's capacity table, write R device indices, the per-device
+demand sums and table'.  Per GPU the batch is fixed (weak scaling); with N > 1 every
+rank scores its own request rows and the ranks exchange their demand vectors with
+one NCCL all-gather, after which each rank applies the summed demand to its replica
+of the table (BASELINE.json north_star).
+
+Timed legs (one JSON line on rank 0):
+  value     device-resident: inputs already in HBM, K steps captured in one CUDA
+            graph (N = 1) and timed with CUDA events on the launching stream;
+            batches rotate through a ring larger than L2.
+  e2e       the same metric through the C-ABI call a cgo caller makes
+            (egpu_bestfit_batch) with pinned HOST buffers: H2D of the requests and
+            D2H of the indices and demand sums inside the timed region.
+  roofline  HBM: algorithmic bytes (12*R + 32*D per launch) / average launch time
+            of the scan kernel in the timed region, against MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (a C port of the spec; the reference has no best-fit
+            loop and no Go toolchain exists here) on the host cores, bounded sample.
+
+--impl reference times that CPU port alone, all host threads, on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "alloc_decisions_per_sec"
+UNIT = "decisions/s"
+RING = 16  # batches in the rotation: 16 x 12 MB (1M rows) = 192 MB > 126 MB L2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_host_batches(e, w, rank, nb, R):
+    out = []
+    for b in range(nb):
+        out.append(e.synth.requests(w["dist"], w["seed"], R, first_row=(rank * nb + b) * R))
+    return out
+
+
+def cpu_port_rate(w, e, R, nthreads, budget_s):
+    """decisions/s of the C oracle port on a bounded sample (first batches of the ring)."""
+    from oracle import oracle_c
+    rc, rm = e.synth.requests(w["dist"], w["seed"], R)
+    fc = np.ascontiguousarray(w["free_core"], dtype=np.int32)
+    fm = np.ascontiguousarray(w["free_mem"], dtype=np.int32)
+    idx = np.empty(R, dtype=np.int32)
+    oracle_c.snapshot_into(fc, fm, rc, rm, idx, nthreads)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle_c.snapshot_into(fc, fm, rc, rm, idx, nthreads)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 200:
+            break
+    return n * R / dt, n
+
+
+def run_reference(args, w, e, rank, world):
+    """The reference arm: the CPU implementation of the path on the host cores.  The
+    reference itself has no best-fit loop and Go is not installed, so
+    this is the oracle port (oracle/bestfit_oracle.c, OpenMP over request rows)."""
+    if rank != 0:
+        return
+    from oracle import oracle_c
+    R = w["R"]
+    threads = oracle_c.max_threads()
+    fc = np.ascontiguousarray(w["free_core"], dtype=np.int32)
+    fm = np.ascontiguousarray(w["free_mem"], dtype=np.int32)
+    batches = make_host_batches(e, w, 0, min(RING, 4), R)
+    idx = np.empty(R, dtype=np.int32)
+    for i in range(args.warmup):
+        rc, rm = batches[i % len(batches)]
+        oracle_c.snapshot_into(fc, fm, rc, rm, idx, threads)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rc, rm = batches[i % len(batches)]
+        oracle_c.snapshot_into(fc, fm, rc, rm, idx, threads)
+    dt = time.perf_counter() - t0
+    val = args.steps * R / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "D": int(w["D"]), "requests_per_step": R,
+                   "note": "CPU port of the builder-defined best-fit spec; the reference repo has no such loop and no Go toolchain is present"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {R} requests, OpenMP over request rows"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="cfg3_1m", help="cfg2 | cfg3 | cfg3_1m | cfg4 | cfg3_64mi")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import elastic_gpu_agent_b200 as e
+    w = e.synth.workload(args.workload)
+
+    if args.impl == "reference":
+        run_reference(args, w, e, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the allocation path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    D, R = int(w["D"]), int(w["R"])
+    alloc = e.BestFitAllocator(local_rank)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    # ---- device-resident ring of batches (larger than L2 in total) ----------
+    nb = RING if R <= (8 << 20) else 2
+    ring = []
+    for b in range(nb):
+        c = torch.empty(R, dtype=torch.int32, device=dev)
+        m = torch.empty(R, dtype=torch.int32, device=dev)
+        alloc.synth_requests_dev(w["dist"], w["seed"], (rank * nb + b) * R, R, c.data_ptr(), m.data_ptr(), sh)
+        ring.append((c, m, torch.empty(R, dtype=torch.int32, device=dev)))
+    delta = torch.zeros(2 * D, dtype=torch.int64, device=dev)
+    gathered = torch.zeros(world * 2 * D, dtype=torch.int64, device=dev)
+    table_out = torch.zeros(3 * D, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        c, m, idx = ring[i % nb]
+        if world == 1:
+            alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), table_out.data_ptr(), False, sh)
+        else:
+            alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, sh)
+            dist.all_gather_into_tensor(gathered, delta)
+            # table' is produced every step but not installed, so every step scores the same table
+            alloc.apply_deltas_dev(gathered.data_ptr(), world, table_out.data_ptr(), False, sh)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+
+    use_graph = (world == 1) and not args.no_graph
+    graph = None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(stream)
+        with torch.cuda.stream(cap):
+            csh = cap.cuda_stream
+            with torch.cuda.graph(graph, stream=cap):
+                for i in range(args.steps):
+                    c, m, idx = ring[i % nb]
+                    alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(),
+                                      table_out.data_ptr(), False, csh)
+        stream.wait_stream(cap)
+        graph.replay()  # warm the instantiated graph once
+        torch.cuda.synchronize()
+
+    launches0 = alloc.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    if graph is not None:
+        graph.replay()
+    else:
+        for i in range(args.steps):
+            step(i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = (alloc.launch_count - launches0) if graph is None else args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * R * args.steps / (ms * 1e-3)
+
+    # correctness spot-check of the timed path against the oracle (rank 0, first batch)
+    parity = None
+    if rank == 0 and R <= (1 << 20):
+        from oracle import oracle_c
+        rc_h, rm_h = e.synth.requests(w["dist"], w["seed"], R, first_row=(rank * nb) * R)
+        exp, *_ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc_h, rm_h, oracle_c.max_threads())
+        if world == 1:
+            got = ring[0][2].cpu().numpy()
+            parity = bool(np.array_equal(got, exp))
+
+    # ---- end-to-end leg: host buffers through the C ABI -----------------------
+    e2e = None
+    e2e_R = R
+    nhb = min(nb, 8) if R <= (8 << 20) else 1
+    host = []
+    for b in range(nhb):
+        rc_h, rm_h = e.synth.requests(w["dist"], w["seed"], e2e_R, first_row=(rank * nb + b) * e2e_R)
+        pc, pm, pi = alloc.pinned_array(e2e_R), alloc.pinned_array(e2e_R), alloc.pinned_array(e2e_R)
+        pc[:] = rc_h
+        pm[:] = rm_h
+        host.append((pc, pm, pi))
+    hdc, hdm = alloc.pinned_array(D, np.int64), alloc.pinned_array(D, np.int64)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        pc, pm, pi = host[i % nhb]
+        alloc.bestfit_raw(pc.ctypes.data, pm.ctypes.data, e2e_R, pi.ctypes.data, hdc.ctypes.data, hdm.ctypes.data)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pc, pm, pi = host[i % nhb]
+        alloc.bestfit_raw(pc.ctypes.data, pm.ctypes.data, e2e_R, pi.ctypes.data, hdc.ctypes.data, hdm.ctypes.data)
+        if world > 1:
+            delta.copy_(torch.from_numpy(np.concatenate([hdc, hdm])), non_blocking=False)
+            dist.all_gather_into_tensor(gathered, delta)
+            _ = gathered.cpu()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e2e = {"value": world * e2e_R * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * e2e_R,
+           "d2h_bytes_per_step": 4 * e2e_R + 16 * D, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+           "api": "egpu_bestfit_batch (C ABI, pinned host buffers)"}
+    if rank == 0 and world == 1 and R <= (1 << 20):
+        from oracle import oracle_c
+        rc_h, rm_h = host[(e2e_steps - 1) % nhb][0], host[(e2e_steps - 1) % nhb][1]
+        exp, *_ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc_h, rm_h, oracle_c.max_threads())
+        parity = bool(parity and np.array_equal(host[(e2e_steps - 1) % nhb][2], exp))
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- sweep over the other BASELINE table sizes (N = 1 only, short) --------
+    sweep = []
+    if rank == 0 and world == 1 and not args.no_sweep:
+        peak, _ = peaks()
+        for name in ["cfg2", "cfg3", "cfg3_1m", "cfg4", "cfg3_64mi"]:
+            if name == args.workload:
+                continue
+            ws = e.synth.workload(name)
+            Rs, Ds = int(ws["R"]), int(ws["D"])
+            nbs = 2 if Rs > (8 << 20) else max(2, min(64, (160 << 20) // (12 * Rs)))
+            alloc.set_table(ws["free_core"], ws["free_mem"])
+            rs = []
+            for b in range(nbs):
+                c = torch.empty(Rs, dtype=torch.int32, device=dev)
+                m = torch.empty(Rs, dtype=torch.int32, device=dev)
+                alloc.synth_requests_dev(ws["dist"], ws["seed"], b * Rs, Rs, c.data_ptr(), m.data_ptr(), sh)
+                rs.append((c, m, torch.empty(Rs, dtype=torch.int32, device=dev)))
+            dl = torch.zeros(2 * Ds, dtype=torch.int64, device=dev)
+            ks = 20 if Rs > (8 << 20) else 200
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream()
+            cap.wait_stream(stream)
+            for i in range(3):
+                c, m, idx = rs[i % nbs]
+                alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), Rs, idx.data_ptr(), dl.data_ptr(), 0, False, sh)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap):
+                    for i in range(ks):
+                        c, m, idx = rs[i % nbs]
+                        alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), Rs, idx.data_ptr(), dl.data_ptr(), 0, False, cap.cuda_stream)
+            stream.wait_stream(cap)
+            g.replay()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            g.replay()
+            a1.record(stream)
+            torch.cuda.synchronize()
+            sms = a0.elapsed_time(a1) / ks
+            gbs = (12 * Rs + 32 * Ds) / (sms * 1e-3) / 1e9
+            sweep.append({"workload": name, "D": Ds, "R": Rs, "us_per_launch": 1e3 * sms,
+                          "decisions_per_s": Rs / (sms * 1e-3), "hbm_gbs": gbs, "frac": gbs / peak,
+                          "l2": "ring > L2" if nbs * 12 * Rs > (126 << 20) else "ring <= L2 (small table)"})
+            del rs, g
+            torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import oracle_c
+        threads = oracle_c.max_threads()
+        Rc = min(R, 1 << 20)
+        v_all, n_all = cpu_port_rate(w, e, Rc, threads, args.cpu_budget)
+        v_one, n_one = cpu_port_rate(w, e, Rc, 1, args.cpu_budget)
+        cpu = {"value": v_all, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_all} passes over {Rc} requests of {args.workload} (C port of the spec, OpenMP over rows, gcc -O3)",
+               "single_thread": {"value": v_one, "cores": 1, "sample": f"{n_one} passes over {Rc} requests, scalar loop"},
+               "note": "reference has no best-fit loop and Go is absent: this is the oracle port, not reference Go"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = 12 * R + 32 * D
+        per_launch_s = (ms * 1e-3) / args.steps
+        achieved = alg_bytes / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {D} devices x {R} requests per GPU per step "
+                                   "(BASELINE metric's largest single-GPU table)" if args.workload == "cfg3_1m"
+                       else f"{args.workload}: {D} devices x {R} requests per GPU per step",
+                       "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
+                       "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
+                             if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
+                       "launch": "CUDA graph of K scan launches" if graph is not None else "eager launches + NCCL all-gather of demand vectors",
+                       "parallelism": f"request rows sharded over {world} GPU(s), table replicated"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "bestfit_sorted_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "avg_launch_us": per_launch_s * 1e6, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "parity_vs_oracle": parity,
+            "sweep": sweep,
+        }
+        print(json.dumps(line), flush=True)
+
+    alloc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI declared in include/egpu_alloc.h.
+
+The library is built in-tree by __graft_entry__.build() (nvcc, sm_100a) as
+elastic-gpu-agent_b200/lib/libegpu_alloc.so.  Importing this module without it
+raises: there is no Python or CPU fallback for the allocation path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libegpu_alloc.so")
+
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+
+OK = 0
+ERR_INVALID = -1
+ERR_NO_DEVICE = -2
+ERR_CUDA = -3
+ERR_NOMEM = -4
+ERR_NO_TABLE = -5
+ERR_STATE = -6
+ERR_PARSE = -7
+ERR_UNSAT = -8
+
+VARIANT_AUTO = 0
+VARIANT_GRID = 1
+VARIANT_SORTED = 2
+
+EV_ALLOC = 0
+EV_FREE = 1
+
+
+class EgpuError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        msg = f"{what}: {strerror(code)} ({code})"
+        if detail:
+            msg += f" [{detail}]"
+        super().__init__(msg)
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    sigs = {
+        "egpu_abi_version": (C.c_int, []),
+        "egpu_strerror": (C.c_char_p, [C.c_int]),
+        "egpu_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "egpu_ctx_destroy": (None, [vp]),
+        "egpu_last_error": (C.c_char_p, [vp]),
+        "egpu_backend": (C.c_int, [vp]),
+        "egpu_launch_count": (C.c_int64, [vp]),
+        "egpu_set_variant": (C.c_int, [vp, C.c_int]),
+        "egpu_table_set": (C.c_int, [vp, i32p, i32p, C.c_int32]),
+        "egpu_table_get": (C.c_int, [vp, i32p, i32p, i32p]),
+        "egpu_table_size": (C.c_int, [vp]),
+        "egpu_bestfit_batch": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int]),
+        "egpu_host_alloc": (C.c_int, [vp, C.POINTER(vp), C.c_int64]),
+        "egpu_host_free": (None, [vp, vp]),
+        "egpu_bestfit_batch_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int, vp]),
+        "egpu_table_apply_deltas_dev": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
+        "egpu_synth_requests_dev": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, vp, vp, vp]),
+        "egpu_replay": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def strerror(code: int) -> str:
+    return load().egpu_strerror(code).decode()

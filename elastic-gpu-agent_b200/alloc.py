@@ -1,0 +1,163 @@
+"""Host-side wrapper of the best-fit allocation path (one context per GPU).
+
+Mirrors the slot the path occupies in the reference: a plugin owns one
+allocator (constructed with the plugin, pkg/plugins/base.go:208-233), commits
+are serialised by a lock (pkg/plugins/gpushare.go:114,239; the lock lives inside
+the C library), errors surface as exceptions the way the Go handlers return
+`error` (pkg/plugins/gpushare.go:41-43).
+
+All compute happens in the CUDA library behind include/egpu_alloc.h; numpy
+arrays here are only the caller-owned host buffers of that C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class BestFitAllocator:
+    """Best-fit device choice over a node-local capacity table on one B200."""
+
+    def __init__(self, cuda_device: int = 0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.egpu_ctx_create(int(cuda_device), C.byref(h))
+        if rc != L.OK:
+            raise L.EgpuError(rc, "egpu_ctx_create")
+        self._h = h
+        self.cuda_device = int(cuda_device)
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.egpu_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def _check(self, rc: int, what: str):
+        if rc != L.OK:
+            raise L.EgpuError(rc, what, self._lib.egpu_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.egpu_launch_count(self._h))
+
+    def set_variant(self, variant: int):
+        self._check(self._lib.egpu_set_variant(self._h, int(variant)), "egpu_set_variant")
+
+    # -- capacity table -----------------------------------------------------
+    def set_table(self, free_core, free_mem):
+        fc, fm = _i32(free_core), _i32(free_mem)
+        if fc.shape != fm.shape or fc.ndim != 1:
+            raise L.EgpuError(L.ERR_INVALID, "set_table")
+        rc = self._lib.egpu_table_set(self._h, fc.ctypes.data_as(L.i32p), fm.ctypes.data_as(L.i32p), fc.size)
+        self._check(rc, "egpu_table_set")
+
+    def table(self):
+        D = self._lib.egpu_table_size(self._h)
+        if D < 0:
+            raise L.EgpuError(D, "egpu_table_size")
+        fc = np.empty(D, dtype=np.int32)
+        fm = np.empty(D, dtype=np.int32)
+        ov = np.empty(D, dtype=np.int32)
+        rc = self._lib.egpu_table_get(self._h, fc.ctypes.data_as(L.i32p), fm.ctypes.data_as(L.i32p),
+                                      ov.ctypes.data_as(L.i32p))
+        self._check(rc, "egpu_table_get")
+        return fc, fm, ov
+
+    # -- snapshot mode, host buffers -----------------------------------------
+    def bestfit(self, req_core, req_mem, commit: bool = False, out_idx: np.ndarray | None = None):
+        """Returns (idx int32[R], delta_core int64[D], delta_mem int64[D])."""
+        rc_, rm_ = _i32(req_core), _i32(req_mem)
+        if rc_.shape != rm_.shape or rc_.ndim != 1:
+            raise L.EgpuError(L.ERR_INVALID, "bestfit")
+        D = self._lib.egpu_table_size(self._h)
+        if D < 0:
+            raise L.EgpuError(D, "egpu_table_size")
+        R = rc_.size
+        idx = out_idx if out_idx is not None else np.empty(R, dtype=np.int32)
+        dc = np.zeros(D, dtype=np.int64)
+        dm = np.zeros(D, dtype=np.int64)
+        rc = self._lib.egpu_bestfit_batch(self._h, _ptr(rc_), _ptr(rm_), R, _ptr(idx), _ptr(dc), _ptr(dm),
+                                          1 if commit else 0)
+        self._check(rc, "egpu_bestfit_batch")
+        return idx, dc, dm
+
+    def bestfit_raw(self, p_core: int, p_mem: int, R: int, p_idx: int, p_dc: int, p_dm: int, commit: bool = False):
+        """Same call on raw host addresses (e.g. pinned buffers from host_alloc)."""
+        rc = self._lib.egpu_bestfit_batch(self._h, C.c_void_p(p_core), C.c_void_p(p_mem), R, C.c_void_p(p_idx),
+                                          C.c_void_p(p_dc), C.c_void_p(p_dm), 1 if commit else 0)
+        self._check(rc, "egpu_bestfit_batch")
+
+    def host_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.egpu_host_alloc(self._h, C.byref(p), int(nbytes)), "egpu_host_alloc")
+        return int(p.value)
+
+    def host_free(self, addr: int):
+        self._lib.egpu_host_free(self._h, C.c_void_p(addr))
+
+    def pinned_array(self, n: int, dtype=np.int32) -> np.ndarray:
+        """numpy view over pinned host memory owned by the context (freed with it
+        only if the caller calls host_free(arr.ctypes.data))."""
+        dt = np.dtype(dtype)
+        addr = self.host_alloc(max(1, n) * dt.itemsize)
+        buf = (C.c_char * (max(1, n) * dt.itemsize)).from_address(addr)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    # -- snapshot mode, device buffers ---------------------------------------
+    def bestfit_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int = 0, d_table_out: int = 0,
+                    commit: bool = False, stream: int = 0):
+        rc = self._lib.egpu_bestfit_batch_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
+                                              C.c_void_p(d_idx), C.c_void_p(d_delta or None),
+                                              C.c_void_p(d_table_out or None), 1 if commit else 0,
+                                              C.c_void_p(stream or None))
+        self._check(rc, "egpu_bestfit_batch_dev")
+
+    def apply_deltas_dev(self, d_deltas: int, G: int, d_table_out: int = 0, commit: bool = True, stream: int = 0):
+        rc = self._lib.egpu_table_apply_deltas_dev(self._h, C.c_void_p(d_deltas), int(G),
+                                                   C.c_void_p(d_table_out or None), 1 if commit else 0,
+                                                   C.c_void_p(stream or None))
+        self._check(rc, "egpu_table_apply_deltas_dev")
+
+    def synth_requests_dev(self, dist: int, seed: int, first_row: int, R: int, d_core: int, d_mem: int,
+                           stream: int = 0):
+        rc = self._lib.egpu_synth_requests_dev(self._h, int(dist), int(seed), int(first_row), int(R),
+                                               C.c_void_p(d_core), C.c_void_p(d_mem), C.c_void_p(stream or None))
+        self._check(rc, "egpu_synth_requests_dev")
+
+    # -- sequential mode ------------------------------------------------------
+    def replay(self, kind, a, b):
+        k, a_, b_ = _i32(kind), _i32(a), _i32(b)
+        if not (k.shape == a_.shape == b_.shape) or k.ndim != 1:
+            raise L.EgpuError(L.ERR_INVALID, "replay")
+        out = np.empty(k.size, dtype=np.int32)
+        rc = self._lib.egpu_replay(self._h, _ptr(k), _ptr(a_), _ptr(b_), k.size, _ptr(out))
+        self._check(rc, "egpu_replay")
+        return out

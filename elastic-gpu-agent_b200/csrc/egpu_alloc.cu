@@ -1,0 +1,845 @@
+// egpu_alloc.cu — best-fit fractional-GPU allocation on B200 (sm_100a) + its C ABI.
+//
+// Product path.  There is no CPU fallback in this file and nothing here
+// includes or links oracle/: when no CUDA device is usable every entry point
+// returns EGPU_ERR_NO_DEVICE.
+//
+// Reference slot this fills: baseDevicePlugin.GetPreferredAllocation, an empty
+// stub in elastic-ai/elastic-gpu-agent (pkg/plugins/base.go:94-96); units from
+// pkg/common/const.go:4 and pkg/plugins/gpushare.go:24-33,159-168.  The decision
+// rule is the builder-defined spec of DESIGN.md §2 (the reference has none).
+#include "egpu_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/egpu_alloc.h"
+
+namespace egpu {
+
+// =============================================================================
+// Snapshot scan
+// =============================================================================
+//
+// Why "sorted" is the fast formulation.  For a fixed table the best-fit device
+// of request (c, m) minimises (fc-c, fm-m, d) over feasible d, which is the same
+// as minimising (fc, fm, d): the request cancels out of the comparison.  So the
+// answer is the FIRST feasible device in the table sorted by (fc, fm, d).  Each
+// CTA sorts the <= 64 table rows once (rank sort in shared memory), every thread
+// keeps the packed sorted rows in registers, and per (request, device) pair the
+// work is: one subtract (both feasibility tests at once, see kGuards), one LOP3
+// producing "sorted position, or a value >= 2^18 if infeasible", and half a
+// 3-input unsigned min (VIMNMX3).  The chosen position maps back to the device
+// index through a shared-memory tile.
+
+template <int DT, int THREADS>
+struct SnapSmem {
+    uint32_t sK[DT];                              // packed table rows, sorted by (fc, fm, d)
+    int32_t sDev[DT + 1];                         // sorted position -> device; [>= D] = -1
+    int32_t sFc[DT];                              // unsorted tile (grid variant)
+    int32_t sFm[DT];
+    unsigned long long sWarpAcc[THREADS / 32][2 * DT];
+    int sLast;
+    unsigned long long hist[THREADS / 32][DT][32];  // lane-private demand sums
+};
+
+template <int DT, int THREADS>
+__device__ __forceinline__ void snapshot_prologue(SnapSmem<DT, THREADS>& s, const DevState* st, int D) {
+    const int tid = threadIdx.x;
+    // zero lane-private accumulators
+    unsigned long long* h = &s.hist[0][0][0];
+    for (int i = tid; i < (THREADS / 32) * DT * 32; i += THREADS) h[i] = 0ull;
+    if (tid < DT) {
+        s.sK[tid] = 0u;
+        s.sDev[tid] = -1;
+        s.sFc[tid] = -1;
+        s.sFm[tid] = -1;
+    }
+    if (tid == 0) s.sDev[DT] = -1;
+    __syncthreads();
+    if (tid < D) {
+        s.sFc[tid] = st->free_core[tid];
+        s.sFm[tid] = st->free_mem[tid];
+    }
+    __syncthreads();
+    if (tid < D) {
+        const int32_t fc = s.sFc[tid];
+        const int32_t fm = s.sFm[tid];
+        // rank sort by (fc, fm, d): position = number of rows that order before this one
+        const uint32_t mine = (static_cast<uint32_t>(fc) << 24) | (static_cast<uint32_t>(fm) << 6) | tid;
+        int pos = 0;
+        for (int k = 0; k < D; ++k) {
+            const uint32_t other = (static_cast<uint32_t>(s.sFc[k]) << 24) |
+                                   (static_cast<uint32_t>(s.sFm[k]) << 6) | k;
+            pos += other < mine;
+        }
+        s.sK[pos] = pack_table_word(fc, fm);
+        s.sDev[pos] = tid;
+    }
+    __syncthreads();
+}
+
+// first feasible sorted position, DT (sentinel) when none
+template <int DT>
+__device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q) {
+    uint32_t best = DT;
+#pragma unroll
+    for (int j = 0; j < DT; j += 2) {
+        const uint32_t t0 = K[j] - q;
+        const uint32_t t1 = K[j + 1] - q;
+        const uint32_t c0 = (~t0 & kGuards) | static_cast<uint32_t>(j);
+        const uint32_t c1 = (~t1 & kGuards) | static_cast<uint32_t>(j + 1);
+        best = __vimin3_u32(best, c0, c1);
+    }
+    return best;
+}
+
+// Demand sums -> global running sums -> (last CTA) delta / table' publication.
+template <int DT, int THREADS>
+__device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
+                                                  long long* __restrict__ delta_out,
+                                                  int32_t* __restrict__ table_out, int flags) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    __syncwarp();
+    for (int d = 0; d < D; ++d) {
+        const unsigned long long v = s.hist[warp][d][lane];
+        const uint32_t c = static_cast<uint32_t>(v >> kAccShift);
+        const uint32_t ml = static_cast<uint32_t>(v) & 0x7FFFFu;
+        const uint32_t mh = static_cast<uint32_t>(v >> 19) & 0x7FFFFu;
+        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
+        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
+        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
+        if (lane == 0) {
+            s.sWarpAcc[warp][d] = sc;
+            s.sWarpAcc[warp][DT + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * D) {
+        const int j = tid < D ? tid : DT + (tid - D);
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) tot += s.sWarpAcc[w][j];
+        if (tot) atomicAdd(&st->acc[tid < D ? tid : kMaxD + (tid - D)], tot);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int ticket = atomicAdd(&st->ticket, 1u);
+        s.sLast = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s.sLast) return;
+    __threadfence();
+    if ((flags & kFlagFinalize) && tid < D) {
+        volatile unsigned long long* acc = st->acc;
+        const long long dc = static_cast<long long>(acc[tid]);
+        const long long dm = static_cast<long long>(acc[kMaxD + tid]);
+        acc[tid] = 0ull;
+        acc[kMaxD + tid] = 0ull;
+        const long long nc = static_cast<long long>(st->free_core[tid]) - dc;
+        const long long nm = static_cast<long long>(st->free_mem[tid]) - dm;
+        const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
+        if (delta_out) {
+            delta_out[tid] = dc;
+            delta_out[D + tid] = dm;
+        }
+        if (table_out) {
+            table_out[tid] = sat_i32(nc);
+            table_out[D + tid] = sat_i32(nm);
+            table_out[2 * D + tid] = over;
+        }
+        if (flags & kFlagCommit) {
+            // the committed table stays inside the spec's domain: negative
+            // leftovers clamp to 0 and the oversubscription flag is sticky
+            st->free_core[tid] = nc < 0 ? 0 : static_cast<int32_t>(nc);
+            st->free_mem[tid] = nm < 0 ? 0 : static_cast<int32_t>(nm);
+            st->oversub[tid] |= over;
+        }
+    }
+    if (tid == 0) st->ticket = 0u;
+}
+
+template <int DT, int THREADS>
+__device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int lane, int32_t idx,
+                                         int32_t core, int32_t mem) {
+    if (idx >= 0) {
+        s.hist[warp][idx][lane] +=
+            (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
+            static_cast<unsigned long long>(static_cast<uint32_t>(mem));
+    }
+}
+
+template <int DT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
+                      const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
+                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int D = st->D;
+
+    const long long nvec = R >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+
+    // issue the first tile's loads before the table is touched: the request
+    // stream is the only HBM traffic that matters
+    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
+    bool has0 = v < nvec, has1 = (v + stride) < nvec;
+    if (has0) {
+        c0 = ld_stream_v4(req_core + 4 * v);
+        m0 = ld_stream_v4(req_mem + 4 * v);
+    }
+    if (has1) {
+        c1 = ld_stream_v4(req_core + 4 * (v + stride));
+        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
+    }
+
+    snapshot_prologue<DT, THREADS>(s, st, D);
+    uint32_t K[DT];
+#pragma unroll
+    for (int j = 0; j < DT; ++j) K[j] = s.sK[j];
+
+    auto decide = [&](int32_t core, int32_t mem) -> int32_t {
+        const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem));
+        const int32_t idx = s.sDev[best > static_cast<uint32_t>(DT) ? DT : best];
+        hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
+        return idx;
+    };
+    auto decide4 = [&](const int4& c, const int4& m) -> int4 {
+        int4 r;
+        r.x = decide(c.x, m.x);
+        r.y = decide(c.y, m.y);
+        r.z = decide(c.z, m.z);
+        r.w = decide(c.w, m.w);
+        return r;
+    };
+
+    while (has0) {
+        const long long vn = v + 2 * stride;
+        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
+        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
+        if (nhas0) {
+            nc0 = ld_stream_v4(req_core + 4 * vn);
+            nm0 = ld_stream_v4(req_mem + 4 * vn);
+        }
+        if (nhas1) {
+            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
+            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
+        }
+        st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
+        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
+        v = vn;
+        has0 = nhas0;
+        has1 = nhas1;
+        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
+    }
+    // ragged tail: R % 4 rows, scalar
+    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
+        const long long r = (nvec << 2) + tid;
+        out_idx[r] = decide(req_core[r], req_mem[r]);
+    }
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags);
+}
+
+// The north-star's literal formulation: every (device, request) pair is scored
+// with the spec's packed key (lc << 24 | lm << 6 | d) against a shared-memory
+// tile of the table and the row is reduced with a running min.  Kept as an
+// independent second device implementation (tests compare the two) and as the
+// baseline the sorted variant is measured against.
+template <int DT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
+                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
+                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int D = st->D;
+    snapshot_prologue<DT, THREADS>(s, st, D);
+
+    auto decide = [&](int32_t core, int32_t mem) -> int32_t {
+        int32_t best = 0x7fffffff;
+        const bool valid = (core | mem) >= 0;
+        for (int d = 0; d < D; ++d) {
+            const int32_t lc = s.sFc[d] - core;
+            const int32_t lm = s.sFm[d] - mem;
+            const int32_t key = (lc << 24) | (lm << 6) | d;
+            best = (valid && (lc | lm) >= 0) ? min(best, key) : best;
+        }
+        const int32_t idx = best == 0x7fffffff ? -1 : (best & 63);
+        hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
+        return idx;
+    };
+
+    const long long nvec = R >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+    for (long long v = static_cast<long long>(blockIdx.x) * THREADS + tid; v < nvec; v += stride) {
+        const int4 c = ld_stream_v4(req_core + 4 * v);
+        const int4 m = ld_stream_v4(req_mem + 4 * v);
+        int4 r;
+        r.x = decide(c.x, m.x);
+        r.y = decide(c.y, m.y);
+        r.z = decide(c.z, m.z);
+        r.w = decide(c.w, m.w);
+        st_stream_v4(out_idx + 4 * v, r);
+    }
+    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
+        const long long r = (nvec << 2) + tid;
+        out_idx[r] = decide(req_core[r], req_mem[r]);
+    }
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags);
+}
+
+// Multi-GPU step 2: table' = table - sum over ranks of their demand vectors.
+__global__ void apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ deltas,
+                                    int G, int32_t* __restrict__ table_out, int commit) {
+    const int D = st->D;
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    long long dc = 0, dm = 0;
+    for (int g = 0; g < G; ++g) {
+        dc += deltas[static_cast<long long>(g) * 2 * D + d];
+        dm += deltas[static_cast<long long>(g) * 2 * D + D + d];
+    }
+    const long long nc = static_cast<long long>(st->free_core[d]) - dc;
+    const long long nm = static_cast<long long>(st->free_mem[d]) - dm;
+    const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
+    if (table_out) {
+        table_out[d] = sat_i32(nc);
+        table_out[D + d] = sat_i32(nm);
+        table_out[2 * D + d] = over;
+    }
+    if (commit) {
+        st->free_core[d] = nc < 0 ? 0 : static_cast<int32_t>(nc);
+        st->free_mem[d] = nm < 0 ? 0 : static_cast<int32_t>(nm);
+        st->oversub[d] |= over;
+    }
+}
+
+// =============================================================================
+// Synthetic request generator (same counter RNG as synth.py)
+// =============================================================================
+__device__ __forceinline__ unsigned long long mix64(unsigned long long seed, unsigned long long stream,
+                                                    unsigned long long i) {
+    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull + i;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ int32_t uniform_i32(unsigned long long seed, unsigned long long stream,
+                                               unsigned long long i, int lo, int hi) {
+    const unsigned long long z = mix64(seed, stream, i);
+    const unsigned long long n = static_cast<unsigned long long>(hi - lo + 1);
+    return lo + static_cast<int32_t>(((z >> 32) * n) >> 32);
+}
+
+__global__ void synth_requests_kernel(int dist, unsigned long long seed, long long first_row, long long R,
+                                      int32_t* __restrict__ req_core, int32_t* __restrict__ req_mem) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < R; k += stride) {
+        const unsigned long long r = static_cast<unsigned long long>(first_row + k);
+        int32_t core, mem;
+        if (dist == 2) {
+            const int ci = uniform_i32(seed, 2, r, 0, 5);
+            const int mi = uniform_i32(seed, 3, r, 0, 6);
+            core = ci == 0 ? 5 : ci == 1 ? 10 : ci == 2 ? 20 : ci == 3 ? 25 : ci == 4 ? 50 : 100;
+            mem = 256 << mi;
+        } else {
+            core = uniform_i32(seed, 2, r, 1, 100);
+            mem = uniform_i32(seed, 3, r, 1, dist == 3 ? 65536 : 24576);
+            if ((r & 15ull) == 15ull) {
+                if (((r >> 4) & 1ull) == 0ull) core = 101;
+                else mem = 183359 + 1;
+            }
+        }
+        req_core[k] = core;
+        req_mem[k] = mem;
+    }
+}
+
+// =============================================================================
+// Sequential mode: one warp, lane = device (two per lane when D > 32)
+// =============================================================================
+//
+// Request k sees the table after k-1: a serial dependence chain, so there is no
+// bandwidth roofline here — the figure of merit is cycles per event.  The warp
+// loads 32 events at a time (coalesced), broadcasts them one by one with
+// shuffles, scores the current table with one packed key per lane and reduces
+// with CREDUX.MIN (__reduce_min_sync).  `live` (device currently held by each
+// ALLOC event, -1 otherwise) sits in shared memory when it fits, else in HBM;
+// only lane 0 touches it, so program order gives consistency.
+constexpr int kReplaySmemEvents = 200 * 1024;
+
+__global__ void __launch_bounds__(32)
+replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const int32_t* __restrict__ ev_a,
+              const int32_t* __restrict__ ev_b, long long E, int32_t* __restrict__ out_idx,
+              signed char* __restrict__ live_global) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    signed char* live = (E <= kReplaySmemEvents) ? reinterpret_cast<signed char*>(smem_raw) : live_global;
+    const int lane = threadIdx.x;
+    const int D = st->D;
+    const int d0 = lane, d1 = lane + 32;
+    int32_t fc0 = d0 < D ? st->free_core[d0] : -1;
+    int32_t fm0 = d0 < D ? st->free_mem[d0] : -1;
+    int32_t fc1 = d1 < D ? st->free_core[d1] : -1;
+    int32_t fm1 = d1 < D ? st->free_mem[d1] : -1;
+
+    for (long long base = 0; base < E; base += 32) {
+        const long long i = base + lane;
+        int32_t k = -1, a = 0, b = 0, ta = 0, tb = 0;
+        bool tvalid = false;
+        if (i < E) {
+            k = kind[i];
+            a = ev_a[i];
+            b = ev_b[i];
+            if (k == 1 && a >= 0 && a < i) {  // gather the released event's request now
+                tvalid = kind[a] == 0;
+                ta = ev_a[a];
+                tb = ev_b[a];
+            }
+        }
+        int32_t my_out = -1;
+        const int n = (E - base) < 32 ? static_cast<int>(E - base) : 32;
+        for (int j = 0; j < n; ++j) {
+            const int32_t kj = __shfl_sync(0xffffffffu, k, j);
+            const int32_t aj = __shfl_sync(0xffffffffu, a, j);
+            const int32_t bj = __shfl_sync(0xffffffffu, b, j);
+            int32_t res = -1;
+            if (kj == 0) {
+                const int32_t lc0 = fc0 - aj, lm0 = fm0 - bj;
+                const int32_t lc1 = fc1 - aj, lm1 = fm1 - bj;
+                const bool valid = (aj | bj) >= 0;
+                int32_t key = 0x7fffffff;
+                if (valid && (lc0 | lm0) >= 0 && fc0 >= 0) key = (lc0 << 24) | (lm0 << 6) | d0;
+                if (valid && (lc1 | lm1) >= 0 && fc1 >= 0) key = min(key, (lc1 << 24) | (lm1 << 6) | d1);
+                const int32_t best = __reduce_min_sync(0xffffffffu, key);
+                if (best != 0x7fffffff) {
+                    res = best & 63;
+                    if (res == d0) { fc0 -= aj; fm0 -= bj; }
+                    if (res == d1) { fc1 -= aj; fm1 -= bj; }
+                }
+                if (lane == 0) live[base + j] = static_cast<signed char>(res);
+            } else {
+                const bool tv = __shfl_sync(0xffffffffu, static_cast<int>(tvalid), j) != 0;
+                const int32_t taj = __shfl_sync(0xffffffffu, ta, j);
+                const int32_t tbj = __shfl_sync(0xffffffffu, tb, j);
+                int32_t dev = -1;
+                if (lane == 0) {
+                    live[base + j] = -1;
+                    if (kj == 1 && tv) {
+                        dev = live[aj];
+                        live[aj] = -1;
+                    }
+                }
+                dev = __shfl_sync(0xffffffffu, dev, 0);
+                if (dev >= 0) {
+                    if (dev == d0) { fc0 += taj; fm0 += tbj; }
+                    if (dev == d1) { fc1 += taj; fm1 += tbj; }
+                }
+                res = dev;
+            }
+            if (lane == j) my_out = res;
+        }
+        if (i < E) out_idx[i] = my_out;
+    }
+    if (d0 < D) { st->free_core[d0] = fc0; st->free_mem[d0] = fm0; }
+    if (d1 < D) { st->free_core[d1] = fc1; st->free_mem[d1] = fm1; }
+}
+
+}  // namespace egpu
+
+// =============================================================================
+// Host side: context + C ABI
+// =============================================================================
+using namespace egpu;
+
+using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int);
+
+struct SnapLaunch {
+    SnapKernel fn = nullptr;
+    int threads = 0;
+    size_t smem = 0;
+    int ctas_per_sm = 0;  // 0 = not configured yet on this context
+};
+
+struct egpu_ctx {
+    std::mutex mu;
+    SnapLaunch snap[2][4];
+    int dev = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    DevState* d_state = nullptr;
+    bool has_table = false;
+    int D = 0;
+    int variant = EGPU_VARIANT_AUTO;
+    int64_t launches = 0;
+    // staging for the host-buffer entry points
+    int32_t* d_req_core = nullptr;
+    int32_t* d_req_mem = nullptr;
+    int32_t* d_idx = nullptr;
+    int64_t d_cap_rows = 0;
+    long long* d_delta = nullptr;     // int64[2*64]
+    int32_t* d_table_out = nullptr;   // int32[3*64]
+    long long* h_delta = nullptr;     // pinned
+    int32_t* h_table = nullptr;       // pinned int32[3*64]
+    signed char* d_live = nullptr;
+    int64_t d_live_cap = 0;
+    char last_err[256] = {0};
+};
+
+namespace {
+
+int cuda_fail(egpu_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) std::snprintf(ctx->last_err, sizeof ctx->last_err, "%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? EGPU_ERR_NOMEM : EGPU_ERR_CUDA;
+}
+
+#define EGPU_CUDA(ctx, call)                                   \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+template <int DT, int THREADS>
+SnapLaunch make_launch(bool grid_variant) {
+    SnapLaunch l;
+    l.fn = grid_variant ? bestfit_grid_kernel<DT, THREADS> : bestfit_sorted_kernel<DT, THREADS>;
+    l.threads = THREADS;
+    l.smem = sizeof(SnapSmem<DT, THREADS>);
+    l.ctas_per_sm = 0;
+    return l;
+}
+
+SnapLaunch pick_launch(int D, bool grid_variant) {
+    if (D <= 8) return make_launch<8, 256>(grid_variant);
+    if (D <= 16) return make_launch<16, 256>(grid_variant);
+    if (D <= 32) return make_launch<32, 256>(grid_variant);
+    return make_launch<64, 128>(grid_variant);
+}
+
+int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
+                    long long* d_delta, int32_t* d_table_out, int flags, cudaStream_t s) {
+    const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
+    const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
+    SnapLaunch& l = ctx->snap[grid_variant ? 1 : 0][bucket];
+    if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
+        l = pick_launch(ctx->D, grid_variant);
+        EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+        int per_sm = 0;
+        EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
+        l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    }
+    // one resident wave at most; each thread takes two 128-bit vectors per trip
+    const int64_t nvec = R >> 2;
+    const int64_t per_cta = static_cast<int64_t>(l.threads) * (grid_variant ? 1 : 2);
+    int64_t want = (nvec + per_cta - 1) / per_cta;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * l.ctas_per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    // lane-private sums hold 2^19 rows per lane (kAccShift): keep rows/thread below that
+    const int64_t rows_per_thread = R / (want * l.threads) + 8;
+    if (rows_per_thread >= (1ll << 19)) return EGPU_ERR_INVALID;
+    l.fn<<<static_cast<unsigned>(want), l.threads, l.smem, s>>>(ctx->d_state, d_rc, d_rm, R, d_idx, d_delta,
+                                                                d_table_out, flags);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return EGPU_OK;
+}
+
+int ensure_staging(egpu_ctx* ctx, int64_t rows) {
+    if (rows <= ctx->d_cap_rows) return EGPU_OK;
+    int64_t cap = ctx->d_cap_rows ? ctx->d_cap_rows : 1024;
+    while (cap < rows) cap *= 2;
+    if (ctx->d_req_core) cudaFree(ctx->d_req_core);
+    if (ctx->d_req_mem) cudaFree(ctx->d_req_mem);
+    if (ctx->d_idx) cudaFree(ctx->d_idx);
+    ctx->d_req_core = ctx->d_req_mem = ctx->d_idx = nullptr;
+    ctx->d_cap_rows = 0;
+    EGPU_CUDA(ctx, cudaMalloc(&ctx->d_req_core, sizeof(int32_t) * cap));
+    EGPU_CUDA(ctx, cudaMalloc(&ctx->d_req_mem, sizeof(int32_t) * cap));
+    EGPU_CUDA(ctx, cudaMalloc(&ctx->d_idx, sizeof(int32_t) * cap));
+    ctx->d_cap_rows = cap;
+    return EGPU_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int egpu_abi_version(void) { return 1000; }
+
+const char* egpu_strerror(int code) {
+    switch (code) {
+        case EGPU_OK: return "ok";
+        case EGPU_ERR_INVALID: return "invalid argument";
+        case EGPU_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case EGPU_ERR_CUDA: return "CUDA runtime error";
+        case EGPU_ERR_NOMEM: return "out of memory";
+        case EGPU_ERR_NO_TABLE: return "capacity table not set";
+        case EGPU_ERR_STATE: return "call not valid in the current state";
+        case EGPU_ERR_PARSE: return "malformed device id";
+        case EGPU_ERR_UNSAT: return "preferred allocation cannot be satisfied";
+        default: return "unknown error";
+    }
+}
+
+int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
+    if (!out) return EGPU_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return EGPU_ERR_NO_DEVICE;
+    }
+    if (cuda_device < 0 || cuda_device >= n) return EGPU_ERR_INVALID;
+    egpu_ctx* ctx = new (std::nothrow) egpu_ctx();
+    if (!ctx) return EGPU_ERR_NOMEM;
+    ctx->dev = cuda_device;
+    int rc = [&]() -> int {
+        EGPU_CUDA(ctx, cudaSetDevice(cuda_device));
+        cudaDeviceProp prop;
+        EGPU_CUDA(ctx, cudaGetDeviceProperties(&prop, cuda_device));
+        ctx->sm_count = prop.multiProcessorCount;
+        EGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_state, sizeof(DevState)));
+        EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_state, 0, sizeof(DevState), ctx->stream));
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_delta, sizeof(long long) * 2 * kMaxD));
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_table_out, sizeof(int32_t) * 3 * kMaxD));
+        EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_delta, sizeof(long long) * 2 * kMaxD));
+        EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_table, sizeof(int32_t) * 3 * kMaxD));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return EGPU_OK;
+    }();
+    if (rc != EGPU_OK) {
+        egpu_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return EGPU_OK;
+}
+
+void egpu_ctx_destroy(egpu_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->dev >= 0) cudaSetDevice(ctx->dev);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaFree(ctx->d_state);
+    cudaFree(ctx->d_req_core);
+    cudaFree(ctx->d_req_mem);
+    cudaFree(ctx->d_idx);
+    cudaFree(ctx->d_delta);
+    cudaFree(ctx->d_table_out);
+    cudaFree(ctx->d_live);
+    if (ctx->h_delta) cudaFreeHost(ctx->h_delta);
+    if (ctx->h_table) cudaFreeHost(ctx->h_table);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+const char* egpu_last_error(egpu_ctx* ctx) { return ctx ? ctx->last_err : ""; }
+int egpu_backend(egpu_ctx* ctx) { return ctx ? 1 : EGPU_ERR_INVALID; }
+int64_t egpu_launch_count(egpu_ctx* ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return ctx->launches;
+}
+
+int egpu_set_variant(egpu_ctx* ctx, int variant) {
+    if (!ctx || variant < EGPU_VARIANT_AUTO || variant > EGPU_VARIANT_SORTED) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->variant = variant;
+    return EGPU_OK;
+}
+
+int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D) {
+    if (!ctx || !free_core || !free_mem || D < 1 || D > EGPU_MAX_DEVICES) return EGPU_ERR_INVALID;
+    for (int d = 0; d < D; ++d) {
+        if (free_core[d] < 0 || free_core[d] > EGPU_CORE_MAX) return EGPU_ERR_INVALID;
+        if (free_mem[d] < 0 || free_mem[d] > EGPU_MEM_MAX) return EGPU_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    DevState h;
+    std::memset(&h, 0, sizeof h);
+    std::memcpy(h.free_core, free_core, sizeof(int32_t) * D);
+    std::memcpy(h.free_mem, free_mem, sizeof(int32_t) * D);
+    h.D = D;
+    // pageable source: the copy is staged before the call returns
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->D = D;
+    ctx->has_table = true;
+    return EGPU_OK;
+}
+
+int egpu_table_size(egpu_ctx* ctx) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return ctx->has_table ? ctx->D : EGPU_ERR_NO_TABLE;
+}
+
+int egpu_table_get(egpu_ctx* ctx, int32_t* free_core, int32_t* free_mem, int32_t* oversub) {
+    if (!ctx || !free_core || !free_mem) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EGPU_CUDA(ctx, cudaMemcpy(ctx->h_table, ctx->d_state, sizeof(int32_t) * 3 * kMaxD, cudaMemcpyDeviceToHost));
+    std::memcpy(free_core, ctx->h_table, sizeof(int32_t) * ctx->D);
+    std::memcpy(free_mem, ctx->h_table + kMaxD, sizeof(int32_t) * ctx->D);
+    if (oversub) std::memcpy(oversub, ctx->h_table + 2 * kMaxD, sizeof(int32_t) * ctx->D);
+    return EGPU_OK;
+}
+
+int egpu_host_alloc(egpu_ctx* ctx, void** out, int64_t bytes) {
+    if (!ctx || !out || bytes <= 0) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    EGPU_CUDA(ctx, cudaMallocHost(out, static_cast<size_t>(bytes)));
+    return EGPU_OK;
+}
+
+void egpu_host_free(egpu_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->dev);
+    cudaFreeHost(p);
+    (void)cudaGetLastError();
+}
+
+int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
+                           int32_t* d_out_idx, int64_t* d_delta, int32_t* d_table_out, int commit,
+                           void* stream) {
+    if (!ctx || R < 0) return EGPU_ERR_INVALID;
+    if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta),
+                           d_table_out, kFlagFinalize | (commit ? kFlagCommit : 0), s);
+}
+
+int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem, int64_t R,
+                       int32_t* out_idx, int64_t* out_delta_core, int64_t* out_delta_mem, int commit) {
+    if (!ctx || R < 0) return EGPU_ERR_INVALID;
+    if (R > 0 && (!req_core || !req_mem || !out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    int rc = ensure_staging(ctx, R > 0 ? R : 1);
+    if (rc != EGPU_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    const int D = ctx->D;
+    if (R > 0) {
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    }
+    rc = launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
+                         kFlagFinalize | (commit ? kFlagCommit : 0), s);
+    if (rc != EGPU_OK) return rc;
+    if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    if (out_delta_core) std::memcpy(out_delta_core, ctx->h_delta, sizeof(int64_t) * D);
+    if (out_delta_mem) std::memcpy(out_delta_mem, ctx->h_delta + D, sizeof(int64_t) * D);
+    return EGPU_OK;
+}
+
+int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G, int32_t* d_table_out,
+                                int commit, void* stream) {
+    if (!ctx || !d_deltas || G < 1) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    apply_deltas_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, reinterpret_cast<const long long*>(d_deltas), G,
+                                            d_table_out, commit);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return EGPU_OK;
+}
+
+int egpu_synth_requests_dev(egpu_ctx* ctx, int dist, uint64_t seed, int64_t first_row, int64_t R,
+                            int32_t* d_req_core, int32_t* d_req_mem, void* stream) {
+    if (!ctx || R < 0 || first_row < 0 || (dist != 2 && dist != 3 && dist != 4)) return EGPU_ERR_INVALID;
+    if (R == 0) return EGPU_OK;
+    if (!d_req_core || !d_req_mem) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int64_t blocks = (R + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    synth_requests_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(dist, seed, first_row, R, d_req_core, d_req_mem);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return EGPU_OK;
+}
+
+int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int32_t* b, int64_t E,
+                int32_t* out_idx) {
+    if (!ctx || E < 0 || E > 0x7fffffffll) return EGPU_ERR_INVALID;
+    if (E > 0 && (!kind || !a || !b || !out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (E == 0) return EGPU_OK;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    // staging: kind -> d_req_core?  three inputs + one output: use own buffers
+    int32_t *d_kind = nullptr, *d_a = nullptr, *d_b = nullptr, *d_out = nullptr;
+    cudaStream_t s = ctx->stream;
+    int rc = [&]() -> int {
+        EGPU_CUDA(ctx, cudaMalloc(&d_kind, sizeof(int32_t) * E));
+        EGPU_CUDA(ctx, cudaMalloc(&d_a, sizeof(int32_t) * E));
+        EGPU_CUDA(ctx, cudaMalloc(&d_b, sizeof(int32_t) * E));
+        EGPU_CUDA(ctx, cudaMalloc(&d_out, sizeof(int32_t) * E));
+        size_t smem = 0;
+        if (E <= kReplaySmemEvents) {
+            smem = static_cast<size_t>((E + 15) & ~15ll);
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                kReplaySmemEvents));
+        } else if (E > ctx->d_live_cap) {
+            cudaFree(ctx->d_live);
+            ctx->d_live = nullptr;
+            ctx->d_live_cap = 0;
+            EGPU_CUDA(ctx, cudaMalloc(&ctx->d_live, static_cast<size_t>(E)));
+            ctx->d_live_cap = E;
+        }
+        EGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+        replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
+        EGPU_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, d_out, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+        return EGPU_OK;
+    }();
+    cudaFree(d_kind);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_out);
+    return rc;
+}
+
+}  // extern "C"

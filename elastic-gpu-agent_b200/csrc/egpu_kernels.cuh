@@ -1,0 +1,80 @@
+// egpu_kernels.cuh — sm_100a kernels of the best-fit allocation path.
+//
+// Everything here is integer compare / subtract / min over int32 arrays that
+// stream through HBM once: 12 algorithmic bytes per decision (two int32 in,
+// one int32 out).  No tensor cores: nothing in this path is a contraction.
+//
+// Layout in HBM:
+//   req_core[R], req_mem[R]  int32, SoA, 16-byte aligned  (read once, 128-bit)
+//   out_idx[R]               int32, 16-byte aligned       (written once, 128-bit)
+//   DevState                 one 2 KiB block: table (free_core, free_mem,
+//                            oversub), running int64 demand sums, ticket
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace egpu {
+
+constexpr int kMaxD = 64;
+constexpr int kCoreMax = 100;
+constexpr int kMemMax = (1 << 18) - 1;
+
+// --- packed compare word (internal; the spec's key is (lc, lm, d)) -----------
+//   bit 26      guard C (1)
+//   bits 19..25 free_core          (7 bits, <= 100)
+//   bit 18      guard M (1)
+//   bits 0..17  free_mem           (18 bits)
+// K - Q with Q = core << 19 | mem keeps both guards iff core <= free_core and
+// mem <= free_mem (each field borrows from its own guard only, because
+// |difference| < field range).  One subtract tests both dimensions.
+constexpr uint32_t kGuardC = 1u << 26;
+constexpr uint32_t kGuardM = 1u << 18;
+constexpr uint32_t kGuards = kGuardC | kGuardM;
+constexpr uint32_t kQInvalid = 127u << 19;  // core 127 > any free_core: infeasible everywhere
+
+// flags of the snapshot kernels
+constexpr int kFlagFinalize = 1;  // last CTA publishes delta / table'
+constexpr int kFlagCommit = 2;    // table' replaces the table
+
+// lane-private demand accumulators pack (core sum << 38 | mem sum) in 64 bits
+constexpr int kAccShift = 38;
+
+struct DevState {
+    int32_t free_core[kMaxD];
+    int32_t free_mem[kMaxD];
+    int32_t oversub[kMaxD];
+    int32_t D;
+    int32_t pad_[3];
+    unsigned long long acc[2 * kMaxD];  // running batch sums: core[0..63], mem[64..127]
+    unsigned int ticket;
+    unsigned int pad2_[3];
+};
+
+__device__ __forceinline__ uint32_t pack_table_word(int32_t fc, int32_t fm) {
+    return kGuardC | (static_cast<uint32_t>(fc) << 19) | kGuardM | static_cast<uint32_t>(fm);
+}
+
+__device__ __forceinline__ uint32_t pack_request_word(int32_t core, int32_t mem) {
+    const bool ok = static_cast<uint32_t>(core) <= 127u && static_cast<uint32_t>(mem) <= static_cast<uint32_t>(kMemMax);
+    return ok ? ((static_cast<uint32_t>(core) << 19) | static_cast<uint32_t>(mem)) : kQInvalid;
+}
+
+// streaming 128-bit accesses: read-once / write-once data stays out of L1
+__device__ __forceinline__ int4 ld_stream_v4(const int32_t* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(int32_t* p, const int4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ int32_t sat_i32(long long v) {
+    return v > 2147483647LL ? 2147483647 : (v < -2147483648LL ? static_cast<int32_t>(-2147483648LL) : static_cast<int32_t>(v));
+}
+
+}  // namespace egpu

@@ -1,0 +1,176 @@
+/*
+ * egpu_alloc.h — C ABI of the B200-native best-fit allocation path.
+ *
+ * This is the drop-in boundary: a Go DaemonSet (elastic-gpu-agent) binds these
+ * symbols through cgo; nothing in the signatures is a CUDA, torch or C++ type.
+ * All pointers are caller-owned and only read/written for the duration of the
+ * call (cgo pointer rule) unless the name ends in `_dev`, in which case they are
+ * CUDA device pointers and the call is asynchronous on the given stream.
+ *
+ * Reference interfaces each entry point stands behind (paths relative to the
+ * reference repo elastic-ai/elastic-gpu-agent @ 2609107):
+ *
+ *   egpu_ctx_create / egpu_ctx_destroy
+ *       constructed where the plugin is built, pkg/manager/manager.go:138
+ *       (plugins.PluginFactory) and pkg/plugins/base.go:208-233.
+ *   egpu_table_set
+ *       the capacity table the reference derives at start-up from NVML:
+ *       pkg/operator/base.go:19-75 (device count, memory bytes),
+ *       pkg/plugins/gpushare.go:24-33 (100 core units per GPU),
+ *       pkg/plugins/gpushare.go:159-168 (one memory unit per MiB).
+ *   egpu_bestfit_batch / egpu_bestfit_batch_dev
+ *       the slot of baseDevicePlugin.GetPreferredAllocation, a stub in the
+ *       reference (pkg/plugins/base.go:94-96); request units follow
+ *       pkg/common/const.go:4 (GPUPercentEachCard = 100) and the vendored
+ *       resource names elasticgpu.io/gpu-core, elasticgpu.io/gpu-memory
+ *       (vendor/elasticgpu.io/elastic-gpu/api/v1alpha1/types.go:105-112).
+ *   egpu_replay
+ *       commits serialised under baseDevicePlugin.lock in PreStartContainer
+ *       (pkg/plugins/gpushare.go:114,239) and frees issued by
+ *       GPUSharePlugin.GC (pkg/plugins/base.go:241-306).
+ *   egpu_preferred_allocation
+ *       pluginapi.PreferredAllocationRequest/Response
+ *       (vendor/k8s.io/kubelet/pkg/apis/deviceplugin/v1beta1/api.pb.go:564-571,
+ *       675-677) with the device-ID format "%d-%02d" of
+ *       pkg/plugins/gpushare.go:28,163.
+ *   egpu_device_hash / egpu_device_hash_batch
+ *       types.NewDevice + hash, pkg/types/device.go:17-25,49-54
+ *       (sort.Strings, join ":", SHA-256, first 8 hex digits), used by
+ *       Allocate (pkg/plugins/gpushare.go:44,179) and by
+ *       KubeletDeviceLocator.Locate (pkg/kube/locator.go:62-90).
+ *
+ * IMPORTANT: the reference contains NO best-fit scoring loop;
+ * the decision rule implemented here is the builder-defined specification in
+ * DESIGN.md §2 ("the spec"), restated on the CPU in oracle/.
+ *
+ * The spec in one paragraph. D devices (1..64), free_core[d] in [0,100]
+ * (percent), free_mem[d] in [0, 2^18-1] (MiB).  Request (core, mem) is feasible
+ * on d iff 0 <= core <= free_core[d] and 0 <= mem <= free_mem[d].  Best fit =
+ * the feasible device with the lexicographically smallest
+ * (free_core[d]-core, free_mem[d]-mem, d); idx = -1 when no device is feasible.
+ * Snapshot mode scores every request of a batch against the same table and
+ * reports per-device demand sums (int64) and table' = table - demand
+ * (saturated to int32, oversub flag when negative).  Sequential mode applies
+ * each event to the table before the next one is scored.
+ */
+#ifndef EGPU_ALLOC_H
+#define EGPU_ALLOC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGPU_MAX_DEVICES   64
+#define EGPU_CORE_MAX      100              /* pkg/common/const.go:4 */
+#define EGPU_MEM_MAX       ((1 << 18) - 1)  /* MiB; B200 reports 183359 */
+#define EGPU_IDX_INFEASIBLE (-1)
+#define EGPU_IDX_DEFERRED   (-2)            /* prefix-commit mode only */
+
+/* return codes: 0 = OK, negative = error, never aborts the process */
+#define EGPU_OK               0
+#define EGPU_ERR_INVALID     (-1)   /* bad argument (NULL, range, D, sizes) */
+#define EGPU_ERR_NO_DEVICE   (-2)   /* no usable CUDA device / driver */
+#define EGPU_ERR_CUDA        (-3)   /* CUDA runtime error (see egpu_last_error) */
+#define EGPU_ERR_NOMEM       (-4)   /* host or device allocation failed */
+#define EGPU_ERR_NO_TABLE    (-5)   /* egpu_table_set has not been called */
+#define EGPU_ERR_STATE       (-6)   /* call not valid in the current state */
+#define EGPU_ERR_PARSE       (-7)   /* malformed device-ID string */
+#define EGPU_ERR_UNSAT       (-8)   /* preferred allocation cannot be satisfied */
+
+/* event kinds for egpu_replay */
+#define EGPU_EV_ALLOC 0
+#define EGPU_EV_FREE  1
+
+/* kernel variants for the snapshot scan (egpu_set_variant) */
+#define EGPU_VARIANT_AUTO    0   /* library picks per D */
+#define EGPU_VARIANT_GRID    1   /* direct (device x request) score grid, min over packed keys */
+#define EGPU_VARIANT_SORTED  2   /* first feasible device in (core, mem, d)-sorted order */
+
+typedef struct egpu_ctx egpu_ctx;
+
+/* ---- lifetime --------------------------------------------------------- */
+
+/* One context per CUDA device (one process per GPU).  Thread-safe: every entry
+ * point takes the context mutex (mirrors baseDevicePlugin.lock) and binds the
+ * CUDA device explicitly, so it may be called from any OS thread (goroutines
+ * migrate).  Fails with EGPU_ERR_NO_DEVICE when there is no GPU: there is NO
+ * CPU fallback in this library. */
+int  egpu_ctx_create(int cuda_device, egpu_ctx** out);
+void egpu_ctx_destroy(egpu_ctx* ctx);
+const char* egpu_strerror(int code);
+/* last CUDA error string seen by this context ("" if none) */
+const char* egpu_last_error(egpu_ctx* ctx);
+/* 1 = CUDA sm_100a path.  (0 is reserved; this library never returns it.) */
+int  egpu_backend(egpu_ctx* ctx);
+/* number of kernels this context has launched since creation */
+int64_t egpu_launch_count(egpu_ctx* ctx);
+int  egpu_set_variant(egpu_ctx* ctx, int variant);
+/* bytes of ABI version: major*1000+minor */
+int  egpu_abi_version(void);
+
+/* ---- capacity table --------------------------------------------------- */
+
+int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core,
+                   const int32_t* free_mem, int32_t D);
+/* oversub may be NULL.  Synchronises the context's stream. */
+int egpu_table_get(egpu_ctx* ctx, int32_t* free_core, int32_t* free_mem,
+                   int32_t* oversub);
+int egpu_table_size(egpu_ctx* ctx);
+
+/* ---- snapshot mode, host buffers (what a cgo caller uses) -------------- */
+
+/* Scores R requests against the current table.  Copies inputs H2D from the
+ * caller's arrays (pinned or pageable), runs the scan, copies idx and deltas
+ * back; returns when the outputs are valid.  out_delta_* have D entries and
+ * may be NULL.  commit != 0 installs table' as the current table. */
+int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core,
+                       const int32_t* req_mem, int64_t R, int32_t* out_idx,
+                       int64_t* out_delta_core, int64_t* out_delta_mem,
+                       int commit);
+
+/* Pinned host memory for callers that want zero staging copies. */
+int  egpu_host_alloc(egpu_ctx* ctx, void** out, int64_t bytes);
+void egpu_host_free(egpu_ctx* ctx, void* p);
+
+/* ---- snapshot mode, device buffers (bench / multi-GPU plumbing) -------- */
+
+/* Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ * context's own stream).  d_delta is int64[2*D]: core sums then mem sums; it
+ * is overwritten, not accumulated.  d_table_out (may be NULL) receives
+ * int32[3*D]: free_core', free_mem', oversub.  commit as above. */
+int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core,
+                           const int32_t* d_req_mem, int64_t R,
+                           int32_t* d_out_idx, int64_t* d_delta,
+                           int32_t* d_table_out, int commit, void* stream);
+
+/* Multi-GPU step 2: after the G per-rank delta vectors (int64[G][2*D], rank
+ * major) have been all-gathered, subtract their sum from the current table on
+ * this rank: d_table_out (may be NULL) receives int32[3*D] as above, and with
+ * commit != 0 the result becomes the current table.  Every rank ends with an
+ * identical table'. */
+int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G,
+                                int32_t* d_table_out, int commit, void* stream);
+
+/* Deterministic synthetic request generator on the device (same counter-based
+ * RNG as the CPU generators).  dist: 2 = cfg2, 3 = cfg3. */
+int egpu_synth_requests_dev(egpu_ctx* ctx, int dist, uint64_t seed,
+                            int64_t first_row, int64_t R, int32_t* d_req_core,
+                            int32_t* d_req_mem, void* stream);
+
+/* ---- sequential mode --------------------------------------------------- */
+
+/* Applies E events in order to the current table (which is updated).
+ * kind[i] = EGPU_EV_ALLOC: a[i] = core, b[i] = mem  -> out_idx[i] = device or -1
+ * kind[i] = EGPU_EV_FREE : a[i] = index of the ALLOC event to release
+ *                          -> out_idx[i] = device released, or -1 when that
+ *                          event is not a live allocation (not an ALLOC, not
+ *                          earlier than i, infeasible, or already freed). */
+int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a,
+                const int32_t* b, int64_t E, int32_t* out_idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGPU_ALLOC_H */

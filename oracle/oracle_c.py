@@ -1,0 +1,87 @@
+"""ctypes loader for oracle/libbestfit_oracle.so (built by oracle/Makefile).
+
+TEST INFRASTRUCTURE ONLY — see oracle/bestfit_oracle.c.  PARITY UNPINNED for the
+best-fit functions (the reference has no such loop).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbestfit_oracle.so")
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        lib = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        lib.oracle_table_valid.restype = C.c_int
+        lib.oracle_table_valid.argtypes = [vp, vp, C.c_int32]
+        lib.oracle_pick_one.restype = C.c_int32
+        lib.oracle_pick_one.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32]
+        lib.oracle_bestfit_snapshot.restype = C.c_int
+        lib.oracle_bestfit_snapshot.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int]
+        lib.oracle_replay.restype = C.c_int
+        lib.oracle_replay.argtypes = [vp, vp, C.c_int32, vp, vp, vp, C.c_int64, vp]
+        lib.oracle_max_threads.restype = C.c_int
+        lib.oracle_max_threads.argtypes = []
+        _lib = lib
+    return _lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def max_threads() -> int:
+    return int(load().oracle_max_threads())
+
+
+def snapshot(free_core, free_mem, req_core, req_mem, nthreads: int = 1):
+    """(idx, delta_core, delta_mem, table_out[3D]) per spec §2.4."""
+    fc, fm, rc, rm = _i32(free_core), _i32(free_mem), _i32(req_core), _i32(req_mem)
+    D, R = fc.size, rc.size
+    idx = np.empty(R, dtype=np.int32)
+    dc = np.zeros(D, dtype=np.int64)
+    dm = np.zeros(D, dtype=np.int64)
+    tab = np.zeros(3 * D, dtype=np.int32)
+    r = load().oracle_bestfit_snapshot(_p(fc), _p(fm), D, _p(rc), _p(rm), R, _p(idx), _p(dc), _p(dm), _p(tab),
+                                       int(nthreads))
+    if r != 0:
+        raise ValueError(f"oracle_bestfit_snapshot failed: {r}")
+    return idx, dc, dm, tab
+
+
+def snapshot_into(fc, fm, rc, rm, idx, nthreads: int):
+    """Timing helper: preallocated int32 arrays, no result marshalling."""
+    r = load().oracle_bestfit_snapshot(_p(fc), _p(fm), fc.size, _p(rc), _p(rm), rc.size, _p(idx), None, None, None,
+                                       int(nthreads))
+    if r != 0:
+        raise ValueError(f"oracle_bestfit_snapshot failed: {r}")
+
+
+def replay(free_core, free_mem, kind, a, b):
+    """(idx, free_core', free_mem') per spec §2.6."""
+    fc, fm = _i32(free_core).copy(), _i32(free_mem).copy()
+    k, a_, b_ = _i32(kind), _i32(a), _i32(b)
+    out = np.empty(k.size, dtype=np.int32)
+    r = load().oracle_replay(_p(fc), _p(fm), fc.size, _p(k), _p(a_), _p(b_), k.size, _p(out))
+    if r != 0:
+        raise ValueError(f"oracle_replay failed: {r}")
+    return out, fc, fm

@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, must be bit-exact
+against the CPU oracle (oracle/) on the same inputs.
+
+"Bit-exact" is against the builder-defined oracle: the reference has no best-fit
+path to compare with — parity unpinned."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "bestfit_kat.json")))
+SYN = json.load(open(os.path.join(HERE, "golden", "bestfit_synth.json")))
+VARIANTS = [1, 2]  # EGPU_VARIANT_GRID, EGPU_VARIANT_SORTED
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def committed(tab, D):
+    """what commit installs: table' with negative leftovers clamped to 0"""
+    return np.maximum(tab[:D], 0), np.maximum(tab[D:2 * D], 0), tab[2 * D:]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("case", KAT["snapshot"], ids=lambda c: c["name"])
+def test_snapshot_kat(case, variant, alloc):
+    alloc.set_variant(variant)
+    alloc.set_table(case["free_core"], case["free_mem"])
+    idx, dc, dm = alloc.bestfit(case["req_core"], case["req_mem"], commit=True)
+    assert idx.tolist() == case["idx"]
+    assert dc.tolist() == case["delta_core"] and dm.tolist() == case["delta_mem"]
+    fc, fm, ov = alloc.table()
+    assert fc.tolist() == [max(v, 0) for v in case["table_core"]]
+    assert fm.tolist() == [max(v, 0) for v in case["table_mem"]]
+    assert ov.tolist() == case["oversub"]
+
+
+@pytest.mark.parametrize("case", KAT["sequential"], ids=lambda c: c["name"])
+def test_sequential_kat(case, alloc):
+    alloc.set_table(case["free_core"], case["free_mem"])
+    idx = alloc.replay(case["kind"], case["a"], case["b"])
+    assert idx.tolist() == case["idx"]
+    fc, fm, _ = alloc.table()
+    assert fc.tolist() == case["table_core"] and fm.tolist() == case["table_mem"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg3_1m", "cfg4"])
+def test_configs_bit_exact_vs_oracle_and_golden(name, variant, alloc, oracle_c, egpu):
+    w = egpu.synth.workload(name)
+    rc, rm = egpu.synth.requests(w["dist"], w["seed"], w["R"])
+    alloc.set_variant(variant)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    idx, dc, dm = alloc.bestfit(rc, rm, commit=True)
+    o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm, 4)
+    assert np.array_equal(idx, o_idx)
+    assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+    g = SYN["snapshot"][name]
+    assert digest(idx) == g["idx_sha256"]
+    assert dc.tolist() == g["delta_core"] and dm.tolist() == g["delta_mem"]
+    fc, fm, ov = alloc.table()
+    efc, efm, eov = committed(o_tab, w["D"])
+    assert np.array_equal(fc, efc) and np.array_equal(fm, efm) and np.array_equal(ov, eov)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("D", [1, 2, 7, 8, 9, 16, 17, 31, 32, 33, 63, 64])
+def test_random_tables_every_device_count(D, variant, alloc, oracle_c, egpu):
+    rng = np.random.default_rng(1000 + D)
+    fc = rng.integers(0, 101, D).astype(np.int32)
+    fm = rng.integers(0, 1 << 18, D).astype(np.int32)
+    R = 40_003  # ragged: not a multiple of 4
+    rc = rng.integers(-1, 104, R).astype(np.int32)
+    rm = rng.integers(-1, (1 << 18) + 2, R).astype(np.int32)
+    rm[::3] = rng.integers(0, 4096, rm[::3].size)  # plenty of feasible rows
+    alloc.set_variant(variant)
+    alloc.set_table(fc, fm)
+    idx, dc, dm = alloc.bestfit(rc, rm)
+    o_idx, o_dc, o_dm, _ = oracle_c.snapshot(fc, fm, rc, rm, 4)
+    assert np.array_equal(idx, o_idx)
+    assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+    # commit=False leaves the table alone
+    fc2, fm2, ov2 = alloc.table()
+    assert np.array_equal(fc2, fc) and np.array_equal(fm2, fm) and not ov2.any()
+
+
+@pytest.mark.parametrize("R", [0, 1, 2, 3, 4, 5, 255, 1023, 1024, 1025, 2049])
+def test_empty_and_ragged_batches(R, alloc, oracle_c, egpu):
+    w = egpu.synth.workload("cfg3")
+    rc, rm = egpu.synth.requests(3, 77, R)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    for variant in VARIANTS:
+        alloc.set_variant(variant)
+        idx, dc, dm = alloc.bestfit(rc, rm)
+        o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm)
+        assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+
+
+def test_ties_pick_lowest_index_everywhere(alloc):
+    for D in (8, 64):
+        alloc.set_table([100] * D, [1000] * D)
+        idx, dc, _ = alloc.bestfit(np.full(4099, 1, np.int32), np.full(4099, 1, np.int32))
+        assert (idx == 0).all() and dc[0] == 4099 and not dc[1:].any()
+
+
+def test_int64_demand_sums_do_not_overflow(alloc, oracle_c):
+    """10^6 rows x 200000 MiB overflows int32; deltas are int64 (spec §2.4)."""
+    R = 1_000_000
+    rc = np.ones(R, np.int32)
+    rm = np.full(R, 200_000, np.int32)
+    alloc.set_table([100, 50], [250_000, 1000])
+    idx, dc, dm = alloc.bestfit(rc, rm, commit=True)
+    assert (idx == 0).all() and dc[0] == R and dm[0] == 200_000 * R
+    fc, fm, ov = alloc.table()
+    assert fc.tolist() == [0, 50] and fm.tolist() == [0, 1000] and ov.tolist() == [1, 0]
+
+
+def test_commit_chain_matches_oracle(alloc, oracle_c, egpu):
+    """commit=1 over several small batches == oracle applied batch by batch."""
+    fc, fm = egpu.synth.table_full(8)
+    alloc.set_table(fc, fm)
+    cur_c, cur_m = fc.copy(), fm.copy()
+    for k in range(6):
+        rc, rm = egpu.synth.requests(2, 100 + k, 7)
+        idx, dc, dm = alloc.bestfit(rc, rm, commit=True)
+        o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(cur_c, cur_m, rc, rm)
+        assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+        cur_c, cur_m, _ = committed(o_tab, 8)
+        g_c, g_m, _ = alloc.table()
+        assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m)
+
+
+def test_churn_replay_cfg5_final_state(alloc, oracle_c, egpu):
+    w = egpu.synth.workload("cfg5")
+    kind, a, b = egpu.synth.churn_events(w["seed"], w["R"])
+    alloc.set_table(w["free_core"], w["free_mem"])
+    idx = alloc.replay(kind, a, b)
+    o_idx, o_fc, o_fm = oracle_c.replay(w["free_core"], w["free_mem"], kind, a, b)
+    assert np.array_equal(idx, o_idx)
+    fc, fm, _ = alloc.table()
+    assert np.array_equal(fc, o_fc) and np.array_equal(fm, o_fm)
+    g = SYN["sequential"]["cfg5_head20000"]
+    assert digest(idx[:g["E"]]) == g["idx_sha256"]
+
+
+@pytest.mark.parametrize("D,E", [(8, 1), (8, 31), (8, 33), (33, 5000), (64, 5000), (8, 300_000)])
+def test_replay_random(D, E, alloc, oracle_c):
+    rng = np.random.default_rng(D * 7919 + E)
+    fc = rng.integers(0, 101, D).astype(np.int32)
+    fm = rng.integers(0, 1 << 18, D).astype(np.int32)
+    kind = (rng.random(E) < 0.45).astype(np.int32)
+    a = np.where(kind == 0, rng.integers(0, 40, E), (rng.random(E) * np.arange(E)).astype(np.int64) - 1).astype(np.int32)
+    b = rng.integers(0, 30000, E).astype(np.int32)
+    kind[rng.integers(0, E, max(1, E // 50))] = 2  # unknown kinds are no-ops
+    alloc.set_table(fc, fm)
+    idx = alloc.replay(kind, a, b)
+    o_idx, o_fc, o_fm = oracle_c.replay(fc, fm, kind, a, b)
+    assert np.array_equal(idx, o_idx)
+    g_c, g_m, _ = alloc.table()
+    assert np.array_equal(g_c, o_fc) and np.array_equal(g_m, o_fm)
+
+
+def test_device_synth_matches_numpy(alloc, egpu):
+    import torch
+    R = 100_003
+    for dist in (2, 3, 4):
+        c = torch.empty(R, dtype=torch.int32, device="cuda")
+        m = torch.empty(R, dtype=torch.int32, device="cuda")
+        alloc.synth_requests_dev(dist, 9, 12345, R, c.data_ptr(), m.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        rc, rm = egpu.synth.requests(dist, 9, R, first_row=12345)
+        assert np.array_equal(c.cpu().numpy(), rc) and np.array_equal(m.cpu().numpy(), rm)
+
+
+def test_device_buffer_entry_point_and_table_out(alloc, oracle_c, egpu):
+    import torch
+    w = egpu.synth.workload("cfg4")
+    R = 262_147
+    rc, rm = egpu.synth.requests(4, 21, R)
+    s = torch.cuda.current_stream().cuda_stream
+    c = torch.from_numpy(rc).cuda()
+    m = torch.from_numpy(rm).cuda()
+    idx = torch.empty(R, dtype=torch.int32, device="cuda")
+    delta = torch.empty(2 * 64, dtype=torch.int64, device="cuda")
+    tab = torch.empty(3 * 64, dtype=torch.int32, device="cuda")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), tab.data_ptr(), False, s)
+    torch.cuda.synchronize()
+    o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm, 4)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert np.array_equal(delta.cpu().numpy(), np.concatenate([o_dc, o_dm]))
+    assert np.array_equal(tab.cpu().numpy(), o_tab)
+
+
+def test_full_size_properties_64mi(alloc, egpu):
+    """BASELINE full size and beyond, checked through size-independent properties:
+    forced-infeasible rows are -1, every chosen device is feasible, the demand
+    sums equal a torch recomputation, and the two kernel variants agree."""
+    import torch
+    w = egpu.synth.workload("cfg3")
+    R = 16 << 20
+    s = torch.cuda.current_stream().cuda_stream
+    c = torch.empty(R, dtype=torch.int32, device="cuda")
+    m = torch.empty(R, dtype=torch.int32, device="cuda")
+    alloc.synth_requests_dev(3, 7, 0, R, c.data_ptr(), m.data_ptr(), s)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    outs = []
+    for variant in VARIANTS:
+        alloc.set_variant(variant)
+        idx = torch.empty(R, dtype=torch.int32, device="cuda")
+        delta = torch.empty(16, dtype=torch.int64, device="cuda")
+        alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, s)
+        torch.cuda.synchronize()
+        outs.append((idx, delta))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    idx, delta = outs[1]
+    assert bool((idx[15::16] == -1).all())
+    fc = torch.tensor(w["free_core"], device="cuda")
+    fm = torch.tensor(w["free_mem"], device="cuda")
+    ok = idx >= 0
+    sel = idx[ok].long()
+    assert bool((fc[sel] >= c[ok]).all()) and bool((fm[sel] >= m[ok]).all())
+    # rows marked infeasible really fit nowhere
+    bad = ~ok
+    fits = ((fc[None, :] >= c[bad][:, None]) & (fm[None, :] >= m[bad][:, None])).any(dim=1)
+    assert not bool(fits.any())
+    dc = torch.zeros(8, dtype=torch.int64, device="cuda").index_add_(0, sel, c[ok].long())
+    dm = torch.zeros(8, dtype=torch.int64, device="cuda").index_add_(0, sel, m[ok].long())
+    assert torch.equal(delta, torch.cat([dc, dm]))
+
+
+def test_error_paths(alloc, egpu):
+    with pytest.raises(egpu.EgpuError) as ei:
+        alloc.bestfit([1], [1])
+    assert ei.value.code == -5  # no table
+    for bad in ([[101], [1]], [[-1], [1]], [[1], [1 << 18]], [[1] * 65, [1] * 65]):
+        with pytest.raises(egpu.EgpuError) as ei:
+            alloc.set_table(*bad)
+        assert ei.value.code == -1
+    assert alloc.launch_count == 0
+    alloc.set_table([1], [1])
+    alloc.bestfit([1], [1])
+    assert alloc.launch_count == 1
