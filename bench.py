@@ -224,7 +224,8 @@ def main():
     def step(i):
         c, m, idx = ring[i % nb]
         if world == 1:
-            alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), table_out.data_ptr(), False, sh)
+            alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), table_out.data_ptr(), False, sh,
+                              inputs_ready=True)
         else:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, sh)
             dist.all_gather_into_tensor(gathered, delta)
@@ -256,7 +257,7 @@ def main():
                 for i in range(args.steps):
                     c, m, idx = ring[i % nb]
                     alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(),
-                                      table_out.data_ptr(), False, csh)
+                                      table_out.data_ptr(), False, csh, inputs_ready=True)
         stream.wait_stream(cap)
         graph.replay()  # warm the instantiated graph once
         torch.cuda.synchronize()
@@ -363,7 +364,8 @@ def main():
                 with torch.cuda.graph(g, stream=cap):
                     for i in range(ks):
                         c, m, idx = rs[i % nbs]
-                        alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), Rs, idx.data_ptr(), dl.data_ptr(), 0, False, cap.cuda_stream)
+                        alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), Rs, idx.data_ptr(), dl.data_ptr(), 0, False,
+                                          cap.cuda_stream, inputs_ready=True)
             stream.wait_stream(cap)
             g.replay()
             torch.cuda.synchronize()

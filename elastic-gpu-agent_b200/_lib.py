@@ -29,6 +29,9 @@ VARIANT_AUTO = 0
 VARIANT_GRID = 1
 VARIANT_SORTED = 2
 
+F_COMMIT = 1
+F_INPUTS_READY = 2
+
 EV_ALLOC = 0
 EV_FREE = 1
 

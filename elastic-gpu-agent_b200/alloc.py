@@ -133,10 +133,11 @@ class BestFitAllocator:
 
     # -- snapshot mode, device buffers ---------------------------------------
     def bestfit_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int = 0, d_table_out: int = 0,
-                    commit: bool = False, stream: int = 0):
+                    commit: bool = False, stream: int = 0, inputs_ready: bool = False):
+        flags = (L.F_COMMIT if commit else 0) | (L.F_INPUTS_READY if inputs_ready else 0)
         rc = self._lib.egpu_bestfit_batch_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
                                               C.c_void_p(d_idx), C.c_void_p(d_delta or None),
-                                              C.c_void_p(d_table_out or None), 1 if commit else 0,
+                                              C.c_void_p(d_table_out or None), flags,
                                               C.c_void_p(stream or None))
         self._check(rc, "egpu_bestfit_batch_dev")
 

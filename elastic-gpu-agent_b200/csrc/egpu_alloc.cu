@@ -38,64 +38,83 @@ namespace egpu {
 
 template <int DT, int THREADS>
 struct SnapSmem {
-    uint32_t sK[DT];                              // packed table rows, sorted by (fc, fm, d)
-    int32_t sDev[DT + 1];                         // sorted position -> device; [>= D] = -1
-    int32_t sFc[DT];                              // unsorted tile (grid variant)
-    int32_t sFm[DT];
+    int32_t sFc[kMaxD];                           // table tile (grid variant; re-sort scratch)
+    int32_t sFm[kMaxD];
+    int32_t sPosDev[kMaxD];
     unsigned long long sWarpAcc[THREADS / 32][2 * DT];
     int sLast;
-    unsigned long long hist[THREADS / 32][DT][32];  // lane-private demand sums
+    int32_t sDevTile[THREADS / 32][DT + 8];           // warp-private: sorted position -> device, [DT] = -1
+    unsigned long long hist[THREADS / 32][DT + 1][32];  // lane-private demand sums; row 0 = "no device"
 };
 
-template <int DT, int THREADS>
-__device__ __forceinline__ void snapshot_prologue(SnapSmem<DT, THREADS>& s, const DevState* st, int D) {
-    const int tid = threadIdx.x;
-    // zero lane-private accumulators
-    unsigned long long* h = &s.hist[0][0][0];
-    for (int i = tid; i < (THREADS / 32) * DT * 32; i += THREADS) h[i] = 0ull;
-    if (tid < DT) {
-        s.sK[tid] = 0u;
-        s.sDev[tid] = -1;
-        s.sFc[tid] = -1;
-        s.sFm[tid] = -1;
-    }
-    if (tid == 0) s.sDev[DT] = -1;
+// Re-derive the sorted view of the table (DevState::sorted_k / sorted_dev /
+// dev_packed).  Called by every thread of ONE CTA after thread d < D has put the
+// new row d into sFc[d] / sFm[d].  Rank sort: position = rows ordering before.
+__device__ __forceinline__ void resort_table_cta(DevState* st, int D, int32_t* sFc, int32_t* sFm,
+                                                 int32_t* sPosDev, int tid) {
+    const int nt = blockDim.x;
     __syncthreads();
-    if (tid < D) {
-        s.sFc[tid] = st->free_core[tid];
-        s.sFm[tid] = st->free_mem[tid];
-    }
+    for (int d = tid; d < kMaxD; d += nt) sPosDev[d] = -1;
     __syncthreads();
-    if (tid < D) {
-        const int32_t fc = s.sFc[tid];
-        const int32_t fm = s.sFm[tid];
-        // rank sort by (fc, fm, d): position = number of rows that order before this one
-        const uint32_t mine = (static_cast<uint32_t>(fc) << 24) | (static_cast<uint32_t>(fm) << 6) | tid;
-        int pos = 0;
-        for (int k = 0; k < D; ++k) {
-            const uint32_t other = (static_cast<uint32_t>(s.sFc[k]) << 24) |
-                                   (static_cast<uint32_t>(s.sFm[k]) << 6) | k;
-            pos += other < mine;
+    for (int d = tid; d < kMaxD; d += nt) {
+        if (d < D) {
+            const int32_t fc = sFc[d], fm = sFm[d];
+            const uint32_t mine = (static_cast<uint32_t>(fc) << 24) | (static_cast<uint32_t>(fm) << 6) | d;
+            int pos = 0;
+            for (int k = 0; k < D; ++k) {
+                const uint32_t other = (static_cast<uint32_t>(sFc[k]) << 24) | (static_cast<uint32_t>(sFm[k]) << 6) | k;
+                pos += other < mine;
+            }
+            st->sorted_k[pos] = pack_table_word(fc, fm);
+            st->sorted_dev[pos] = d;
+            sPosDev[pos] = d;
+        } else {  // positions >= D are never produced by a rank
+            st->sorted_k[d] = 0u;
+            st->sorted_dev[d] = -1;
         }
-        s.sK[pos] = pack_table_word(fc, fm);
-        s.sDev[pos] = tid;
     }
     __syncthreads();
+    if (tid == 0) {
+        unsigned long long packed = 0;
+        for (int j = 0; j < 8; ++j)
+            packed |= static_cast<unsigned long long>(static_cast<uint32_t>(sPosDev[j]) & 0xffu) << (8 * j);
+        st->dev_packed = packed;
+    }
 }
 
 // first feasible sorted position, DT (sentinel) when none
 template <int DT>
 __device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q) {
+    // candidate = sorted position j when both guards survived K[j] - q, else j + (missing
+    // guards) >= 2^18.  Written as (G + j) - (t & G): one subtract, one LOP3, one add per
+    // pair (ptxas spreads the adds over the FMA and ALU pipes) and half a VIMNMX3.
     uint32_t best = DT;
 #pragma unroll
     for (int j = 0; j < DT; j += 2) {
-        const uint32_t t0 = K[j] - q;
-        const uint32_t t1 = K[j + 1] - q;
-        const uint32_t c0 = (~t0 & kGuards) | static_cast<uint32_t>(j);
-        const uint32_t c1 = (~t1 & kGuards) | static_cast<uint32_t>(j + 1);
+        const uint32_t w0 = (K[j] - q) & kGuards;
+        const uint32_t w1 = (K[j + 1] - q) & kGuards;
+        const uint32_t c0 = (kGuards + static_cast<uint32_t>(j)) - w0;
+        const uint32_t c1 = (kGuards + static_cast<uint32_t>(j + 1)) - w1;
         best = __vimin3_u32(best, c0, c1);
     }
     return best;
+}
+
+template <int DT, int THREADS>
+__device__ __forceinline__ void hist_zero(SnapSmem<DT, THREADS>& s, int warp, int lane) {
+    // lane-private: each lane clears exactly the words it will use -> no barrier
+#pragma unroll
+    for (int d = 0; d <= DT; ++d) s.hist[warp][d][lane] = 0ull;
+}
+
+template <int DT, int THREADS>
+__device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int lane, int32_t idx,
+                                         int32_t core, int32_t mem) {
+    // unconditional: infeasible rows (idx = -1) land in the dummy row 0, whose
+    // content is never read (it may hold garbage from out-of-domain requests)
+    s.hist[warp][idx + 1][lane] +=
+        (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
+        static_cast<unsigned long long>(static_cast<uint32_t>(mem));
 }
 
 // Demand sums -> global running sums -> (last CTA) delta / table' publication.
@@ -108,7 +127,7 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     const int warp = tid >> 5;
     __syncwarp();
     for (int d = 0; d < D; ++d) {
-        const unsigned long long v = s.hist[warp][d][lane];
+        const unsigned long long v = s.hist[warp][d + 1][lane];
         const uint32_t c = static_cast<uint32_t>(v >> kAccShift);
         const uint32_t ml = static_cast<uint32_t>(v) & 0x7FFFFu;
         const uint32_t mh = static_cast<uint32_t>(v >> 19) & 0x7FFFFu;
@@ -127,8 +146,8 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) tot += s.sWarpAcc[w][j];
         if (tot) atomicAdd(&st->acc[tid < D ? tid : kMaxD + (tid - D)], tot);
+        __threadfence();  // only the threads that published sums need to order them before the ticket
     }
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned int ticket = atomicAdd(&st->ticket, 1u);
@@ -137,7 +156,9 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     __syncthreads();
     if (!s.sLast) return;
     __threadfence();
-    if ((flags & kFlagFinalize) && tid < D) {
+    const bool fin = (flags & kFlagFinalize) != 0;
+    const bool commit = fin && (flags & kFlagCommit);
+    if (fin && tid < D) {
         volatile unsigned long long* acc = st->acc;
         const long long dc = static_cast<long long>(acc[tid]);
         const long long dm = static_cast<long long>(acc[kMaxD + tid]);
@@ -155,25 +176,20 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
             table_out[D + tid] = sat_i32(nm);
             table_out[2 * D + tid] = over;
         }
-        if (flags & kFlagCommit) {
+        if (commit) {
             // the committed table stays inside the spec's domain: negative
             // leftovers clamp to 0 and the oversubscription flag is sticky
-            st->free_core[tid] = nc < 0 ? 0 : static_cast<int32_t>(nc);
-            st->free_mem[tid] = nm < 0 ? 0 : static_cast<int32_t>(nm);
+            const int32_t cc = nc < 0 ? 0 : static_cast<int32_t>(nc);
+            const int32_t cm = nm < 0 ? 0 : static_cast<int32_t>(nm);
+            st->free_core[tid] = cc;
+            st->free_mem[tid] = cm;
             st->oversub[tid] |= over;
+            s.sFc[tid] = cc;
+            s.sFm[tid] = cm;
         }
     }
+    if (commit) resort_table_cta(st, D, s.sFc, s.sFm, s.sPosDev, tid);
     if (tid == 0) st->ticket = 0u;
-}
-
-template <int DT, int THREADS>
-__device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int lane, int32_t idx,
-                                         int32_t core, int32_t mem) {
-    if (idx >= 0) {
-        s.hist[warp][idx][lane] +=
-            (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-            static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-    }
 }
 
 template <int DT, int THREADS>
@@ -186,14 +202,18 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int D = st->D;
+    const bool late = (flags & kFlagLateWait) != 0;
+    if (!late) {  // predecessor may have produced our inputs or changed the table
+        pdl_wait();
+        pdl_trigger();
+    }
 
     const long long nvec = R >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * THREADS;
     long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
 
-    // issue the first tile's loads before the table is touched: the request
-    // stream is the only HBM traffic that matters
+    // issue the first tile's loads before anything else: the request stream is
+    // the only HBM traffic that matters
     int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
     bool has0 = v < nvec, has1 = (v + stride) < nvec;
     if (has0) {
@@ -205,14 +225,23 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         m1 = ld_stream_v4(req_mem + 4 * (v + stride));
     }
 
-    snapshot_prologue<DT, THREADS>(s, st, D);
+    // sorted table rows: uniform loads straight into registers, no barrier
+    const int D = st->D;
     uint32_t K[DT];
 #pragma unroll
-    for (int j = 0; j < DT; ++j) K[j] = s.sK[j];
+    for (int j = 0; j < DT; j += 4) {
+        const uint4 k4 = *reinterpret_cast<const uint4*>(&st->sorted_k[j]);
+        K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
+    }
+    // warp-private tile of the position -> device map: only a warp-level barrier
+    int32_t* tile = s.sDevTile[warp];
+    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
+    hist_zero<DT, THREADS>(s, warp, lane);
+    __syncwarp();
 
     auto decide = [&](int32_t core, int32_t mem) -> int32_t {
         const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem));
-        const int32_t idx = s.sDev[best > static_cast<uint32_t>(DT) ? DT : best];
+        const int32_t idx = tile[best];  // best <= DT; tile[DT] = -1
         hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
         return idx;
     };
@@ -249,6 +278,10 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
+    if (late) {  // the running sums and the ticket belong to the previous launch until it is done
+        pdl_wait();
+        pdl_trigger();
+    }
     snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags);
 }
 
@@ -267,8 +300,15 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    pdl_wait();
+    pdl_trigger();
     const int D = st->D;
-    snapshot_prologue<DT, THREADS>(s, st, D);
+    hist_zero<DT, THREADS>(s, warp, lane);
+    if (tid < D) {
+        s.sFc[tid] = st->free_core[tid];
+        s.sFm[tid] = st->free_mem[tid];
+    }
+    __syncthreads();
 
     auto decide = [&](int32_t core, int32_t mem) -> int32_t {
         int32_t best = 0x7fffffff;
@@ -304,29 +344,37 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
 }
 
 // Multi-GPU step 2: table' = table - sum over ranks of their demand vectors.
-__global__ void apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ deltas,
-                                    int G, int32_t* __restrict__ table_out, int commit) {
+__global__ void __launch_bounds__(kMaxD)
+apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ deltas,
+                    int G, int32_t* __restrict__ table_out, int commit) {
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     const int D = st->D;
     const int d = threadIdx.x;
-    if (d >= D) return;
-    long long dc = 0, dm = 0;
-    for (int g = 0; g < G; ++g) {
-        dc += deltas[static_cast<long long>(g) * 2 * D + d];
-        dm += deltas[static_cast<long long>(g) * 2 * D + D + d];
+    if (d < D) {
+        long long dc = 0, dm = 0;
+        for (int g = 0; g < G; ++g) {
+            dc += deltas[static_cast<long long>(g) * 2 * D + d];
+            dm += deltas[static_cast<long long>(g) * 2 * D + D + d];
+        }
+        const long long nc = static_cast<long long>(st->free_core[d]) - dc;
+        const long long nm = static_cast<long long>(st->free_mem[d]) - dm;
+        const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
+        if (table_out) {
+            table_out[d] = sat_i32(nc);
+            table_out[D + d] = sat_i32(nm);
+            table_out[2 * D + d] = over;
+        }
+        if (commit) {
+            const int32_t cc = nc < 0 ? 0 : static_cast<int32_t>(nc);
+            const int32_t cm = nm < 0 ? 0 : static_cast<int32_t>(nm);
+            st->free_core[d] = cc;
+            st->free_mem[d] = cm;
+            st->oversub[d] |= over;
+            sFc[d] = cc;
+            sFm[d] = cm;
+        }
     }
-    const long long nc = static_cast<long long>(st->free_core[d]) - dc;
-    const long long nm = static_cast<long long>(st->free_mem[d]) - dm;
-    const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
-    if (table_out) {
-        table_out[d] = sat_i32(nc);
-        table_out[D + d] = sat_i32(nm);
-        table_out[2 * D + d] = over;
-    }
-    if (commit) {
-        st->free_core[d] = nc < 0 ? 0 : static_cast<int32_t>(nc);
-        st->free_mem[d] = nm < 0 ? 0 : static_cast<int32_t>(nm);
-        st->oversub[d] |= over;
-    }
+    if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, d);
 }
 
 // =============================================================================
@@ -455,8 +503,10 @@ replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const
         }
         if (i < E) out_idx[i] = my_out;
     }
-    if (d0 < D) { st->free_core[d0] = fc0; st->free_mem[d0] = fm0; }
-    if (d1 < D) { st->free_core[d1] = fc1; st->free_mem[d1] = fm1; }
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    if (d0 < D) { st->free_core[d0] = fc0; st->free_mem[d0] = fm0; sFc[d0] = fc0; sFm[d0] = fm0; }
+    if (d1 < D) { st->free_core[d1] = fc1; st->free_mem[d1] = fm1; sFc[d1] = fc1; sFm[d1] = fm1; }
+    resort_table_cta(st, D, sFc, sFm, sPosDev, lane);
 }
 
 }  // namespace egpu
@@ -497,6 +547,11 @@ struct egpu_ctx {
     int32_t* h_table = nullptr;       // pinned int32[3*64]
     signed char* d_live = nullptr;
     int64_t d_live_cap = 0;
+    // bookkeeping for programmatic dependent launch (see launch_snapshot)
+    bool prev_is_scan = false;        // the last kernel this context launched was a snapshot scan ...
+    bool prev_changes_table = false;  // ... and it may rewrite the table (commit)
+    cudaStream_t prev_stream = nullptr;
+    uintptr_t prev_out_lo = 0, prev_out_hi = 0;
     char last_err[256] = {0};
 };
 
@@ -531,8 +586,32 @@ SnapLaunch pick_launch(int D, bool grid_variant) {
     return make_launch<64, 128>(grid_variant);
 }
 
+// host copy of resort_table_cta: sorted view of a freshly set table
+void fill_sorted(DevState& h) {
+    const int D = h.D;
+    for (int j = 0; j < kMaxD; ++j) {
+        h.sorted_k[j] = 0u;
+        h.sorted_dev[j] = -1;
+    }
+    unsigned long long packed = ~0ull;
+    for (int d = 0; d < D; ++d) {
+        const uint32_t mine = (static_cast<uint32_t>(h.free_core[d]) << 24) | (static_cast<uint32_t>(h.free_mem[d]) << 6) | d;
+        int pos = 0;
+        for (int k = 0; k < D; ++k) {
+            const uint32_t other = (static_cast<uint32_t>(h.free_core[k]) << 24) | (static_cast<uint32_t>(h.free_mem[k]) << 6) | k;
+            pos += other < mine;
+        }
+        h.sorted_k[pos] = pack_table_word(h.free_core[d], h.free_mem[d]);
+        h.sorted_dev[pos] = d;
+        if (pos < 8) packed = (packed & ~(0xffull << (8 * pos))) | (static_cast<unsigned long long>(d) << (8 * pos));
+    }
+    h.dev_packed = packed;
+}
+
+// user_flags: EGPU_F_COMMIT | EGPU_F_INPUTS_READY.  finalize = 0 only for the
+// chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
-                    long long* d_delta, int32_t* d_table_out, int flags, cudaStream_t s) {
+                    long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
     SnapLaunch& l = ctx->snap[grid_variant ? 1 : 0][bucket];
@@ -553,10 +632,42 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // lane-private sums hold 2^19 rows per lane (kAccShift): keep rows/thread below that
     const int64_t rows_per_thread = R / (want * l.threads) + 8;
     if (rows_per_thread >= (1ll << 19)) return EGPU_ERR_INVALID;
-    l.fn<<<static_cast<unsigned>(want), l.threads, l.smem, s>>>(ctx->d_state, d_rc, d_rm, R, d_idx, d_delta,
-                                                                d_table_out, flags);
-    EGPU_CUDA(ctx, cudaGetLastError());
+
+    int flags = (finalize ? kFlagFinalize : 0) | ((user_flags & EGPU_F_COMMIT) ? kFlagCommit : 0);
+    // Programmatic dependent launch.  Every scan is launched with the PDL
+    // attribute, so it may be scheduled while its predecessor drains.  By
+    // default it still waits (griddepcontrol.wait) before touching anything.
+    // It may run its whole scan first and wait only before the epilogue when
+    //  - the caller vouches its inputs were complete before the previous launch
+    //    on this stream (EGPU_F_INPUTS_READY),
+    //  - that previous launch was a scan of this context on the same stream
+    //    that does not rewrite the table, and
+    //  - the two launches write disjoint index ranges.
+    const uintptr_t out_lo = reinterpret_cast<uintptr_t>(d_idx);
+    const uintptr_t out_hi = out_lo + static_cast<uintptr_t>(R) * sizeof(int32_t);
+    const bool disjoint = out_hi <= ctx->prev_out_lo || ctx->prev_out_hi <= out_lo;
+    if (!grid_variant && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan && !ctx->prev_changes_table &&
+        ctx->prev_stream == s && disjoint)
+        flags |= kFlagLateWait;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(want));
+    cfg.blockDim = dim3(static_cast<unsigned>(l.threads));
+    cfg.dynamicSmemBytes = l.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
+                                      d_delta, d_table_out, flags));
     ctx->launches += 1;
+    ctx->prev_is_scan = true;
+    ctx->prev_changes_table = (flags & kFlagCommit) != 0;
+    ctx->prev_stream = s;
+    ctx->prev_out_lo = out_lo;
+    ctx->prev_out_hi = out_hi;
     return EGPU_OK;
 }
 
@@ -683,11 +794,13 @@ int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_
     std::memcpy(h.free_core, free_core, sizeof(int32_t) * D);
     std::memcpy(h.free_mem, free_mem, sizeof(int32_t) * D);
     h.D = D;
+    fill_sorted(h);
     // pageable source: the copy is staged before the call returns
     EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->D = D;
     ctx->has_table = true;
+    ctx->prev_is_scan = false;
     return EGPU_OK;
 }
 
@@ -727,7 +840,7 @@ void egpu_host_free(egpu_ctx* ctx, void* p) {
 }
 
 int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
-                           int32_t* d_out_idx, int64_t* d_delta, int32_t* d_table_out, int commit,
+                           int32_t* d_out_idx, int64_t* d_delta, int32_t* d_table_out, int flags,
                            void* stream) {
     if (!ctx || R < 0) return EGPU_ERR_INVALID;
     if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
@@ -737,7 +850,7 @@ int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta),
-                           d_table_out, kFlagFinalize | (commit ? kFlagCommit : 0), s);
+                           d_table_out, flags, true, s);
 }
 
 int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem, int64_t R,
@@ -756,7 +869,7 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
         EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
     }
     rc = launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
-                         kFlagFinalize | (commit ? kFlagCommit : 0), s);
+                         commit ? EGPU_F_COMMIT : 0, true, s);
     if (rc != EGPU_OK) return rc;
     if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
     EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));
@@ -773,6 +886,7 @@ int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G, i
     if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    ctx->prev_is_scan = false;
     apply_deltas_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, reinterpret_cast<const long long*>(d_deltas), G,
                                             d_table_out, commit);
     EGPU_CUDA(ctx, cudaGetLastError());
@@ -791,6 +905,7 @@ int egpu_synth_requests_dev(egpu_ctx* ctx, int dist, uint64_t seed, int64_t firs
     int64_t blocks = (R + 255) / 256;
     const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
     if (blocks > cap) blocks = cap;
+    ctx->prev_is_scan = false;
     synth_requests_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(dist, seed, first_row, R, d_req_core, d_req_mem);
     EGPU_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
@@ -828,6 +943,7 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+        ctx->prev_is_scan = false;
         replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
         EGPU_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;

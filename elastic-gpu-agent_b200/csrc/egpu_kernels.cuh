@@ -35,6 +35,8 @@ constexpr uint32_t kQInvalid = 127u << 19;  // core 127 > any free_core: infeasi
 // flags of the snapshot kernels
 constexpr int kFlagFinalize = 1;  // last CTA publishes delta / table'
 constexpr int kFlagCommit = 2;    // table' replaces the table
+constexpr int kFlagLateWait = 4;  // programmatic dependent launch: overlap the scan with the
+                                  // previous launch's tail, wait only before the epilogue
 
 // lane-private demand accumulators pack (core sum << 38 | mem sum) in 64 bits
 constexpr int kAccShift = 38;
@@ -43,20 +45,28 @@ struct DevState {
     int32_t free_core[kMaxD];
     int32_t free_mem[kMaxD];
     int32_t oversub[kMaxD];
+    // derived, refreshed whenever the table changes: rows sorted by (fc, fm, d)
+    uint32_t sorted_k[kMaxD];             // packed compare words, 0 past D
+    int32_t sorted_dev[kMaxD];            // sorted position -> device, -1 past D
+    unsigned long long dev_packed;        // D <= 8: byte j = device at position j (0xff = none)
     int32_t D;
-    int32_t pad_[3];
+    int32_t pad_[1];
     unsigned long long acc[2 * kMaxD];  // running batch sums: core[0..63], mem[64..127]
     unsigned int ticket;
     unsigned int pad2_[3];
 };
 
-__device__ __forceinline__ uint32_t pack_table_word(int32_t fc, int32_t fm) {
+__host__ __device__ __forceinline__ uint32_t pack_table_word(int32_t fc, int32_t fm) {
     return kGuardC | (static_cast<uint32_t>(fc) << 19) | kGuardM | static_cast<uint32_t>(fm);
 }
 
 __device__ __forceinline__ uint32_t pack_request_word(int32_t core, int32_t mem) {
-    const bool ok = static_cast<uint32_t>(core) <= 127u && static_cast<uint32_t>(mem) <= static_cast<uint32_t>(kMemMax);
-    return ok ? ((static_cast<uint32_t>(core) << 19) | static_cast<uint32_t>(mem)) : kQInvalid;
+    // out-of-domain values clamp to "infeasible everywhere": a negative int is a huge
+    // unsigned; core 127 exceeds every free_core (<= 100); mem 2^18 clears guard M of
+    // every table word (free_mem + 2^18 - 2^18 < 2^18) without touching the core field
+    const uint32_t c = min(static_cast<uint32_t>(core), 127u);
+    const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
+    return (c << 19) + m;
 }
 
 // streaming 128-bit accesses: read-once / write-once data stays out of L1
@@ -72,6 +82,12 @@ __device__ __forceinline__ void st_stream_v4(int32_t* p, const int4& v) {
                  "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+
+// programmatic dependent launch (PDL): the next launch in the stream may start
+// once every CTA of this one has executed the trigger; `wait` blocks until the
+// previous launch has completed and its writes are visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ int32_t sat_i32(long long v) {
     return v > 2147483647LL ? 2147483647 : (v < -2147483648LL ? static_cast<int32_t>(-2147483648LL) : static_cast<int32_t>(v));

@@ -83,6 +83,12 @@ extern "C" {
 #define EGPU_EV_ALLOC 0
 #define EGPU_EV_FREE  1
 
+/* flags of egpu_bestfit_batch_dev */
+#define EGPU_F_COMMIT        1   /* table' replaces the current table */
+#define EGPU_F_INPUTS_READY  2   /* the request arrays were complete before the previous
+                                    launch on this stream: the scan may overlap that
+                                    launch's tail (programmatic dependent launch) */
+
 /* kernel variants for the snapshot scan (egpu_set_variant) */
 #define EGPU_VARIANT_AUTO    0   /* library picks per D */
 #define EGPU_VARIANT_GRID    1   /* direct (device x request) score grid, min over packed keys */
@@ -139,11 +145,12 @@ void egpu_host_free(egpu_ctx* ctx, void* p);
 /* Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
  * context's own stream).  d_delta is int64[2*D]: core sums then mem sums; it
  * is overwritten, not accumulated.  d_table_out (may be NULL) receives
- * int32[3*D]: free_core', free_mem', oversub.  commit as above. */
+ * int32[3*D]: free_core', free_mem', oversub.  flags: EGPU_F_*.  The three
+ * request/index arrays must be 16-byte aligned (128-bit accesses). */
 int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                            const int32_t* d_req_mem, int64_t R,
                            int32_t* d_out_idx, int64_t* d_delta,
-                           int32_t* d_table_out, int commit, void* stream);
+                           int32_t* d_table_out, int flags, void* stream);
 
 /* Multi-GPU step 2: after the G per-rank delta vectors (int64[G][2*D], rank
  * major) have been all-gathered, subtract their sum from the current table on

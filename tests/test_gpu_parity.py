@@ -198,6 +198,52 @@ def test_device_buffer_entry_point_and_table_out(alloc, oracle_c, egpu):
     assert np.array_equal(tab.cpu().numpy(), o_tab)
 
 
+@pytest.mark.parametrize("D", [8, 64])
+def test_pipelined_launches_overlap_safely(D, alloc, oracle_c, egpu):
+    """EGPU_F_INPUTS_READY lets consecutive scans overlap (programmatic dependent
+    launch).  A chain of 24 batches over a ring of buffers, with a commit in the
+    middle and one launch that reuses the previous output buffer, must equal the
+    oracle applied batch by batch."""
+    import torch
+    rng = np.random.default_rng(D)
+    fc = rng.integers(20, 101, D).astype(np.int32)
+    fm = rng.integers(1 << 15, 1 << 18, D).astype(np.int32)
+    s = torch.cuda.current_stream().cuda_stream
+    R = 60_001
+    nb = 6
+    host = [egpu.synth.requests(4, 300 + b, R) for b in range(nb)]
+    dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(m).cuda()) for c, m in host]
+    outs = [torch.empty(R + 3, dtype=torch.int32, device="cuda") for _ in range(nb)]
+    deltas = [torch.empty(2 * D, dtype=torch.int64, device="cuda") for _ in range(24)]
+    torch.cuda.synchronize()
+    alloc.set_table(fc, fm)
+    plan = []
+    for i in range(24):
+        b = i % nb
+        ob = b if i != 13 else (i - 1) % nb      # launch 13 writes where launch 12 wrote
+        commit = i in (7, 8, 20)
+        plan.append((b, ob, commit))
+        alloc.bestfit_dev(dev[b][0].data_ptr(), dev[b][1].data_ptr(), R, outs[ob].data_ptr(), deltas[i].data_ptr(), 0,
+                          commit, s, inputs_ready=True)
+    torch.cuda.synchronize()
+    # replay on the oracle; only the LAST writer of each output buffer is checkable
+    cur_c, cur_m = fc.copy(), fm.copy()
+    last_writer = {}
+    expect = []
+    for i, (b, ob, commit) in enumerate(plan):
+        o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(cur_c, cur_m, host[b][0], host[b][1], 4)
+        expect.append((o_idx, np.concatenate([o_dc, o_dm])))
+        last_writer[ob] = i
+        if commit:
+            cur_c, cur_m, _ = committed(o_tab, D)
+    for i in range(24):
+        assert np.array_equal(deltas[i].cpu().numpy(), expect[i][1]), f"delta of launch {i}"
+    for ob, i in last_writer.items():
+        assert np.array_equal(outs[ob][:R].cpu().numpy(), expect[i][0]), f"indices of launch {i}"
+    g_c, g_m, _ = alloc.table()
+    assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m)
+
+
 def test_full_size_properties_64mi(alloc, egpu):
     """BASELINE full size and beyond, checked through size-independent properties:
     forced-infeasible rows are -1, every chosen device is feasible, the demand
