@@ -121,7 +121,8 @@ __device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int
 template <int DT, int THREADS>
 __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
                                                   long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags) {
+                                                  int32_t* __restrict__ table_out, int flags, int slot) {
+    DevState::EpiSlot& ep = st->epi[slot];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -145,12 +146,12 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
         unsigned long long tot = 0;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) tot += s.sWarpAcc[w][j];
-        if (tot) atomicAdd(&st->acc[tid < D ? tid : kMaxD + (tid - D)], tot);
+        if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
         __threadfence();  // only the threads that published sums need to order them before the ticket
     }
     __syncthreads();
     if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&st->ticket, 1u);
+        const unsigned int ticket = atomicAdd(&ep.ticket, 1u);
         s.sLast = (ticket == gridDim.x - 1);
     }
     __syncthreads();
@@ -159,7 +160,7 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     const bool fin = (flags & kFlagFinalize) != 0;
     const bool commit = fin && (flags & kFlagCommit);
     if (fin && tid < D) {
-        volatile unsigned long long* acc = st->acc;
+        volatile unsigned long long* acc = ep.acc;
         const long long dc = static_cast<long long>(acc[tid]);
         const long long dm = static_cast<long long>(acc[kMaxD + tid]);
         acc[tid] = 0ull;
@@ -189,24 +190,22 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
         }
     }
     if (commit) resort_table_cta(st, D, s.sFc, s.sFm, s.sPosDev, tid);
-    if (tid == 0) st->ticket = 0u;
+    if (tid == 0) ep.ticket = 0u;
 }
 
 template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags) {
+                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const bool late = (flags & kFlagLateWait) != 0;
-    if (!late) {  // predecessor may have produced our inputs or changed the table
-        pdl_wait();
-        pdl_trigger();
-    }
+    if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
+    pdl_trigger();
 
     const long long nvec = R >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * THREADS;
@@ -278,11 +277,8 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    if (late) {  // the running sums and the ticket belong to the previous launch until it is done
-        pdl_wait();
-        pdl_trigger();
-    }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot);
+    if (late) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
 }
 
 // The north-star's literal formulation: every (device, request) pair is scored
@@ -294,7 +290,7 @@ template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                     const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags) {
+                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -340,7 +336,7 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot);
 }
 
 // Multi-GPU step 2: table' = table - sum over ranks of their demand vectors.
@@ -516,7 +512,7 @@ replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const
 // =============================================================================
 using namespace egpu;
 
-using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int);
+using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int, int);
 
 struct SnapLaunch {
     SnapKernel fn = nullptr;
@@ -544,6 +540,8 @@ struct egpu_ctx {
     long long* d_delta = nullptr;     // int64[2*64]
     int32_t* d_table_out = nullptr;   // int32[3*64]
     long long* h_delta = nullptr;     // pinned
+    long long* h_delta_dev = nullptr; // its device-visible alias
+    bool no_zero_copy = false;        // EGPU_NO_ZERO_COPY=1: always stage through HBM
     int32_t* h_table = nullptr;       // pinned int32[3*64]
     signed char* d_live = nullptr;
     int64_t d_live_cap = 0;
@@ -551,7 +549,12 @@ struct egpu_ctx {
     bool prev_is_scan = false;        // the last kernel this context launched was a snapshot scan ...
     bool prev_changes_table = false;  // ... and it may rewrite the table (commit)
     cudaStream_t prev_stream = nullptr;
-    uintptr_t prev_out_lo = 0, prev_out_hi = 0;
+    uint64_t seq = 0;                 // scans launched (epilogue slot = seq mod kEpiSlots)
+    int group_len = 0;                // launches since (and including) the last fully ordered one
+    struct Range { uintptr_t lo, hi; } group_out[3 * kPipeGroupMax];  // their output ranges
+    int pipe_group = 16;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
+    int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
+    int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     char last_err[256] = {0};
 };
 
@@ -611,7 +614,8 @@ void fill_sorted(DevState& h) {
 // user_flags: EGPU_F_COMMIT | EGPU_F_INPUTS_READY.  finalize = 0 only for the
 // chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
-                    long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s) {
+                    long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
+                    int rpt_hint = 0) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
     SnapLaunch& l = ctx->snap[grid_variant ? 1 : 0][bucket];
@@ -622,33 +626,54 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
         l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
     }
-    // one resident wave at most; each thread takes two 128-bit vectors per trip
+    int flags = (finalize ? kFlagFinalize : 0) | ((user_flags & EGPU_F_COMMIT) ? kFlagCommit : 0);
+    // Programmatic dependent launch.  Every scan carries the PDL attribute, so the
+    // hardware may schedule it while its predecessor is still running.  A fully
+    // ordered launch waits (griddepcontrol.wait) before it touches anything.  A
+    // pipelined launch (kFlagLateWait) runs scan and epilogue at once — its epilogue
+    // state is its own slot — and waits only before exiting.  That is allowed when
+    //  - the caller vouches its inputs were complete before the previous launch on
+    //    this stream (EGPU_F_INPUTS_READY),
+    //  - the previous launch was a scan of this context on the same stream that
+    //    does not rewrite the table, and this one is a plain finalising scan,
+    //  - its outputs (indices, demand sums, table') are disjoint from the outputs
+    //    of every launch since the last fully ordered one, and
+    //  - fewer than pipe_group launches have been issued since then, which bounds
+    //    the launches in flight to pipe_group + 1 < kEpiSlots.
+    egpu_ctx::Range mine[3] = {
+        {reinterpret_cast<uintptr_t>(d_idx), reinterpret_cast<uintptr_t>(d_idx) + static_cast<uintptr_t>(R) * sizeof(int32_t)},
+        {reinterpret_cast<uintptr_t>(d_delta), reinterpret_cast<uintptr_t>(d_delta) + (d_delta ? sizeof(long long) * 2 * ctx->D : 0)},
+        {reinterpret_cast<uintptr_t>(d_table_out), reinterpret_cast<uintptr_t>(d_table_out) + (d_table_out ? sizeof(int32_t) * 3 * ctx->D : 0)}};
+    bool pipelined = !grid_variant && finalize && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan &&
+                     !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0 &&
+                     ctx->group_len < ctx->pipe_group;
+    for (int i = 0; pipelined && i < 3 * ctx->group_len; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (mine[k].lo < ctx->group_out[i].hi && ctx->group_out[i].lo < mine[k].hi) pipelined = false;
+    if (pipelined) flags |= kFlagLateWait;
+    else ctx->group_len = 0;
+    const int slot = finalize ? static_cast<int>(ctx->seq % kEpiSlots) : kEpiSlots;
+
+    // Grid: one resident wave at most.  A lone launch wants every SM pulling at once
+    // (8 rows per thread, one trip); launches of a pipelined stream overlap each
+    // other, so a smaller grid with more rows per thread (48) costs fewer CTA
+    // launches, fewer atomics and leaves room for the neighbours — measured best on
+    // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
-    const int64_t per_cta = static_cast<int64_t>(l.threads) * (grid_variant ? 1 : 2);
+    int rpt = ((user_flags & EGPU_F_INPUTS_READY) && ctx->D <= 16) ? 48 : 8;
+    if (rpt_hint > 0) rpt = rpt_hint;
+    if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
+    if (grid_variant) rpt = 4;
+    const int64_t per_cta = static_cast<int64_t>(l.threads) * ((rpt + 3) / 4);
     int64_t want = (nvec + per_cta - 1) / per_cta;
-    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * l.ctas_per_sm;
+    int per_sm = l.ctas_per_sm;
+    if (ctx->ctas_per_sm_cap > 0 && ctx->ctas_per_sm_cap < per_sm) per_sm = ctx->ctas_per_sm_cap;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     // lane-private sums hold 2^19 rows per lane (kAccShift): keep rows/thread below that
     const int64_t rows_per_thread = R / (want * l.threads) + 8;
     if (rows_per_thread >= (1ll << 19)) return EGPU_ERR_INVALID;
-
-    int flags = (finalize ? kFlagFinalize : 0) | ((user_flags & EGPU_F_COMMIT) ? kFlagCommit : 0);
-    // Programmatic dependent launch.  Every scan is launched with the PDL
-    // attribute, so it may be scheduled while its predecessor drains.  By
-    // default it still waits (griddepcontrol.wait) before touching anything.
-    // It may run its whole scan first and wait only before the epilogue when
-    //  - the caller vouches its inputs were complete before the previous launch
-    //    on this stream (EGPU_F_INPUTS_READY),
-    //  - that previous launch was a scan of this context on the same stream
-    //    that does not rewrite the table, and
-    //  - the two launches write disjoint index ranges.
-    const uintptr_t out_lo = reinterpret_cast<uintptr_t>(d_idx);
-    const uintptr_t out_hi = out_lo + static_cast<uintptr_t>(R) * sizeof(int32_t);
-    const bool disjoint = out_hi <= ctx->prev_out_lo || ctx->prev_out_hi <= out_lo;
-    if (!grid_variant && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan && !ctx->prev_changes_table &&
-        ctx->prev_stream == s && disjoint)
-        flags |= kFlagLateWait;
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(want));
@@ -661,13 +686,14 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
-                                      d_delta, d_table_out, flags));
+                                      d_delta, d_table_out, flags, slot));
     ctx->launches += 1;
-    ctx->prev_is_scan = true;
+    ctx->seq += 1;
+    for (int k = 0; k < 3; ++k) ctx->group_out[3 * ctx->group_len + k] = mine[k];
+    ctx->group_len += 1;
+    ctx->prev_is_scan = finalize;
     ctx->prev_changes_table = (flags & kFlagCommit) != 0;
     ctx->prev_stream = s;
-    ctx->prev_out_lo = out_lo;
-    ctx->prev_out_hi = out_hi;
     return EGPU_OK;
 }
 
@@ -688,6 +714,16 @@ int ensure_staging(egpu_ctx* ctx, int64_t rows) {
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// device-visible alias of a pinned (mapped) host allocation, nullptr for anything else
+void* mapped_alias(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
 
 }  // namespace
 
@@ -728,12 +764,20 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         cudaDeviceProp prop;
         EGPU_CUDA(ctx, cudaGetDeviceProperties(&prop, cuda_device));
         ctx->sm_count = prop.multiProcessorCount;
+        if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
+        if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
+        if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {
+            const int g = std::atoi(e);
+            ctx->pipe_group = g < 1 ? 1 : (g > kPipeGroupMax ? kPipeGroupMax : g);
+        }
         EGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_state, sizeof(DevState)));
         EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_state, 0, sizeof(DevState), ctx->stream));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_delta, sizeof(long long) * 2 * kMaxD));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_table_out, sizeof(int32_t) * 3 * kMaxD));
         EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_delta, sizeof(long long) * 2 * kMaxD));
+        EGPU_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_delta_dev), ctx->h_delta, 0));
+        if (const char* e = std::getenv("EGPU_NO_ZERO_COPY")) ctx->no_zero_copy = std::atoi(e) != 0;
         EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_table, sizeof(int32_t) * 3 * kMaxD));
         EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return EGPU_OK;
@@ -860,20 +904,36 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
-    int rc = ensure_staging(ctx, R > 0 ? R : 1);
-    if (rc != EGPU_OK) return rc;
     cudaStream_t s = ctx->stream;
     const int D = ctx->D;
-    if (R > 0) {
-        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
-        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    int rc;
+    // Zero-copy: when all three caller arrays are pinned (egpu_host_alloc or
+    // cudaHostRegister) and 16-byte aligned, the scan reads the requests and writes
+    // the indices straight across PCIe — one launch, no staging in HBM, reads and
+    // writes overlap on the full-duplex link.  Demand sums land in pinned memory too.
+    const int32_t* zc = R > 0 ? static_cast<const int32_t*>(mapped_alias(req_core)) : nullptr;
+    const int32_t* zm = R > 0 ? static_cast<const int32_t*>(mapped_alias(req_mem)) : nullptr;
+    int32_t* zi = R > 0 ? static_cast<int32_t*>(mapped_alias(out_idx)) : nullptr;
+    if (zc && zm && zi && aligned16(zc) && aligned16(zm) && aligned16(zi) && !ctx->no_zero_copy) {
+        // 64 rows per thread: few CTAs, many trips, so reads of later rows and writes of
+        // earlier ones are on the link at the same time (PCIe is full duplex)
+        rc = launch_snapshot(ctx, zc, zm, R, zi, ctx->h_delta_dev, nullptr, commit ? EGPU_F_COMMIT : 0, true, s, 64);
+        if (rc != EGPU_OK) return rc;
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    } else {
+        rc = ensure_staging(ctx, R > 0 ? R : 1);
+        if (rc != EGPU_OK) return rc;
+        if (R > 0) {
+            EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+            EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        }
+        rc = launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
+                             commit ? EGPU_F_COMMIT : 0, true, s);
+        if (rc != EGPU_OK) return rc;
+        if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
     }
-    rc = launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
-                         commit ? EGPU_F_COMMIT : 0, true, s);
-    if (rc != EGPU_OK) return rc;
-    if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
-    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));
-    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
     if (out_delta_core) std::memcpy(out_delta_core, ctx->h_delta, sizeof(int64_t) * D);
     if (out_delta_mem) std::memcpy(out_delta_mem, ctx->h_delta + D, sizeof(int64_t) * D);
     return EGPU_OK;

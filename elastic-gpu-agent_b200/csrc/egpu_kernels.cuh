@@ -35,8 +35,10 @@ constexpr uint32_t kQInvalid = 127u << 19;  // core 127 > any free_core: infeasi
 // flags of the snapshot kernels
 constexpr int kFlagFinalize = 1;  // last CTA publishes delta / table'
 constexpr int kFlagCommit = 2;    // table' replaces the table
-constexpr int kFlagLateWait = 4;  // programmatic dependent launch: overlap the scan with the
-                                  // previous launch's tail, wait only before the epilogue
+constexpr int kFlagLateWait = 4;  // programmatic dependent launch: this launch shares nothing
+                                  // with the launches in flight before it, so it triggers its
+                                  // successor at once and waits for its predecessor only
+                                  // before it exits (stream order is kept, nothing else)
 
 // lane-private demand accumulators pack (core sum << 38 | mem sum) in 64 bits
 constexpr int kAccShift = 38;
@@ -51,10 +53,16 @@ struct DevState {
     unsigned long long dev_packed;        // D <= 8: byte j = device at position j (0xff = none)
     int32_t D;
     int32_t pad_[1];
-    unsigned long long acc[2 * kMaxD];  // running batch sums: core[0..63], mem[64..127]
-    unsigned int ticket;
-    unsigned int pad2_[3];
+    // Epilogue state is per launch (slot = launch sequence mod kEpiSlots): several scans may
+    // be in flight at once and each needs its own running sums and arrival ticket.
+    struct EpiSlot {
+        unsigned long long acc[2 * kMaxD];  // running batch sums: core[0..63], mem[64..127]
+        unsigned int ticket;
+        unsigned int pad_[3];
+    } epi[33];
 };
+constexpr int kEpiSlots = 32;      // ring used by pipelined launches; slot 32 = accumulate-only launches
+constexpr int kPipeGroupMax = 24;  // at most this many launches between two fully ordered ones
 
 __host__ __device__ __forceinline__ uint32_t pack_table_word(int32_t fc, int32_t fm) {
     return kGuardC | (static_cast<uint32_t>(fc) << 19) | kGuardM | static_cast<uint32_t>(fm);

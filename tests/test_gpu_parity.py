@@ -102,6 +102,32 @@ def test_empty_and_ragged_batches(R, alloc, oracle_c, egpu):
         assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
 
 
+@pytest.mark.parametrize("D,dist", [(8, 3), (64, 4)])
+def test_zero_copy_pinned_buffers(D, dist, alloc, oracle_c, egpu):
+    """Pinned caller buffers take the zero-copy path (the scan reads/writes host memory
+    across PCIe); a misaligned pinned slice must fall back to staging.  Same answers."""
+    w = egpu.synth.workload("cfg3" if D == 8 else "cfg4")
+    R = 300_001
+    rc, rm = egpu.synth.requests(dist, 55, R)
+    pc, pm, pi = alloc.pinned_array(R + 8), alloc.pinned_array(R + 8), alloc.pinned_array(R + 8)
+    dc, dm = alloc.pinned_array(D, np.int64), alloc.pinned_array(D, np.int64)
+    o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm, 4)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    for off in (0, 1, 4):  # element offsets: 0 and 4 are 16-byte aligned, 1 is not
+        pc[off:off + R] = rc
+        pm[off:off + R] = rm
+        pi[:] = -9
+        n0 = alloc.launch_count
+        alloc.bestfit_raw(pc.ctypes.data + 4 * off, pm.ctypes.data + 4 * off, R, pi.ctypes.data + 4 * off,
+                          dc.ctypes.data, dm.ctypes.data)
+        assert alloc.launch_count == n0 + 1
+        assert np.array_equal(pi[off:off + R], o_idx)
+        assert (pi[:off] == -9).all() and (pi[off + R:] == -9).all()
+        assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+    for a in (pc, pm, pi, dc, dm):
+        alloc.host_free(a.ctypes.data)
+
+
 def test_ties_pick_lowest_index_everywhere(alloc):
     for D in (8, 64):
         alloc.set_table([100] * D, [1000] * D)
@@ -242,6 +268,51 @@ def test_pipelined_launches_overlap_safely(D, alloc, oracle_c, egpu):
         assert np.array_equal(outs[ob][:R].cpu().numpy(), expect[i][0]), f"indices of launch {i}"
     g_c, g_m, _ = alloc.table()
     assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m)
+
+
+def test_pipelined_launches_many_small_batches(alloc, oracle_c, egpu):
+    """Hundreds of tiny batches back to back (each one CTA): many launches could be in
+    flight at once; the launch groups bound that and results stay exact.  Also a run
+    where every launch shares ONE demand-sum buffer (must fall back to ordered launches:
+    the buffer ends up holding the last launch's sums)."""
+    import torch
+    w = egpu.synth.workload("cfg3")
+    s = torch.cuda.current_stream().cuda_stream
+    n, R = 300, 513
+    rc, rm = egpu.synth.requests(3, 41, n * R)
+    c = torch.from_numpy(rc).cuda()
+    m = torch.from_numpy(rm).cuda()
+    stride = 516  # 513 rows * 4 B is not a multiple of 16: batch k sits at a 16-byte aligned offset
+    idx = torch.full((n * stride,), -7, dtype=torch.int32, device="cuda")
+    deltas = torch.zeros(n, 16, dtype=torch.int64, device="cuda")
+    shared = torch.zeros(16, dtype=torch.int64, device="cuda")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    torch.cuda.synchronize()
+    idx2 = torch.full((n * stride,), -7, dtype=torch.int32, device="cuda")
+    c2 = torch.zeros(n * stride, dtype=torch.int32, device="cuda")
+    m2 = torch.zeros(n * stride, dtype=torch.int32, device="cuda")
+    for k in range(n):
+        c2[k * stride:k * stride + R] = c[k * R:(k + 1) * R]
+        m2[k * stride:k * stride + R] = m[k * R:(k + 1) * R]
+    torch.cuda.synchronize()
+    for k in range(n):
+        o = 4 * k * stride
+        alloc.bestfit_dev(c2.data_ptr() + o, m2.data_ptr() + o, R, idx2.data_ptr() + o, deltas[k].data_ptr(), 0, False, s,
+                          inputs_ready=True)
+    for k in range(n):
+        o = 4 * k * stride
+        alloc.bestfit_dev(c2.data_ptr() + o, m2.data_ptr() + o, R, idx.data_ptr() + o, shared.data_ptr(), 0, False, s,
+                          inputs_ready=True)
+    torch.cuda.synchronize()
+    got = idx2.cpu().numpy().reshape(n, stride)
+    got_b = idx.cpu().numpy().reshape(n, stride)
+    dl = deltas.cpu().numpy()
+    for k in range(n):
+        o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc[k * R:(k + 1) * R], rm[k * R:(k + 1) * R])
+        assert np.array_equal(got[k, :R], o_idx) and (got[k, R:] == -7).all()
+        assert np.array_equal(got_b[k, :R], o_idx)
+        assert np.array_equal(dl[k], np.concatenate([o_dc, o_dm]))
+    assert np.array_equal(shared.cpu().numpy(), dl[n - 1])
 
 
 def test_full_size_properties_64mi(alloc, egpu):
