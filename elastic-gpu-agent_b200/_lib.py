@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libegpu_alloc.so")
+# EGPU_LIB_PATH: experiments only (an alternative build of the same sources)
+LIB_PATH = os.environ.get("EGPU_LIB_PATH") or os.path.join(_HERE, "lib", "libegpu_alloc.so")
 
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)
@@ -28,6 +29,7 @@ ERR_UNSAT = -8
 VARIANT_AUTO = 0
 VARIANT_GRID = 1
 VARIANT_SORTED = 2
+VARIANT_LUT = 3
 
 F_COMMIT = 1
 F_INPUTS_READY = 2

@@ -10,6 +10,7 @@
 // rule is the builder-defined spec of DESIGN.md §2 (the reference has none).
 #include "egpu_kernels.cuh"
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,11 +66,11 @@ __device__ __forceinline__ void resort_table_cta(DevState* st, int D, int32_t* s
                 const uint32_t other = (static_cast<uint32_t>(sFc[k]) << 24) | (static_cast<uint32_t>(sFm[k]) << 6) | k;
                 pos += other < mine;
             }
-            st->sorted_k[pos] = pack_table_word(fc, fm);
+            st->sorted_k[pos] = pack_table_word(fc, fm) | (static_cast<uint32_t>(pos) & 31u);
             st->sorted_dev[pos] = d;
             sPosDev[pos] = d;
         } else {  // positions >= D are never produced by a rank
-            st->sorted_k[d] = 0u;
+            st->sorted_k[d] = kPadWord;
             st->sorted_dev[d] = -1;
         }
     }
@@ -82,22 +83,29 @@ __device__ __forceinline__ void resort_table_cta(DevState* st, int D, int32_t* s
     }
 }
 
-// first feasible sorted position, DT (sentinel) when none
-template <int DT>
-__device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q) {
-    // candidate = sorted position j when both guards survived K[j] - q, else j + (missing
-    // guards) >= 2^18.  Written as (G + j) - (t & G): one subtract, one LOP3, one add per
-    // pair (ptxas spreads the adds over the FMA and ALU pipes) and half a VIMNMX3.
-    uint32_t best = DT;
+// First feasible sorted position; >= DT when there is none.
+// Per (request, row) pair: one subtract (IMAD.IADD or IADD3, ptxas balances the FMA and
+// ALU pipes), one 3-input LOP3 ((t ^ G) & M, both masks in registers), half a VIMNMX3.
+template <int N>
+__device__ __forceinline__ uint32_t first_feasible32(const uint32_t* K, uint32_t q, uint32_t gx, uint32_t gm) {
+    uint32_t best = kNoCand;
 #pragma unroll
-    for (int j = 0; j < DT; j += 2) {
-        const uint32_t w0 = (K[j] - q) & kGuards;
-        const uint32_t w1 = (K[j + 1] - q) & kGuards;
-        const uint32_t c0 = (kGuards + static_cast<uint32_t>(j)) - w0;
-        const uint32_t c1 = (kGuards + static_cast<uint32_t>(j + 1)) - w1;
+    for (int j = 0; j < N; j += 2) {
+        const uint32_t c0 = ((K[j] - q) ^ gx) & gm;
+        const uint32_t c1 = ((K[j + 1] - q) ^ gx) & gm;
         best = __vimin3_u32(best, c0, c1);
     }
-    return best;
+    return best;  // 0..N-1, or >= 32
+}
+template <int DT>
+__device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q, uint32_t gx, uint32_t gm) {
+    if constexpr (DT <= 32) {
+        return min(first_feasible32<DT>(K, q, gx, gm), static_cast<uint32_t>(DT));
+    } else {  // positions are stored mod 32: two halves
+        const uint32_t lo = first_feasible32<32>(K, q, gx, gm);
+        const uint32_t hi = first_feasible32<DT - 32>(K + 32, q, gx, gm);
+        return lo < 32u ? lo : (hi < 32u ? 32u + hi : static_cast<uint32_t>(DT));
+    }
 }
 
 template <int DT, int THREADS>
@@ -117,45 +125,33 @@ __device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int
         static_cast<unsigned long long>(static_cast<uint32_t>(mem));
 }
 
-// Demand sums -> global running sums -> (last CTA) delta / table' publication.
-template <int DT, int THREADS>
-__device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
-                                                  long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags, int slot) {
+// Second half of every snapshot epilogue.  `wacc` holds per-warp demand sums in shared
+// memory: core sum of device d of warp w at wacc[w * wstride + core_off + d], mem sum at
+// [... + mem_off + d].  Called by all threads after a __syncthreads().  Publishes the CTA's
+// sums with one red.global.add.u64 per device, takes an arrival ticket, and the last CTA
+// writes delta / table', optionally commits (and re-sorts) the table and resets the slot.
+template <int WARPS>
+__device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
+                                                 int32_t* sFc, int32_t* sFm, int32_t* sPosDev, int* sLast,
+                                                 DevState* st, int D, long long* __restrict__ delta_out,
+                                                 int32_t* __restrict__ table_out, int flags, int slot) {
     DevState::EpiSlot& ep = st->epi[slot];
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    __syncwarp();
-    for (int d = 0; d < D; ++d) {
-        const unsigned long long v = s.hist[warp][d + 1][lane];
-        const uint32_t c = static_cast<uint32_t>(v >> kAccShift);
-        const uint32_t ml = static_cast<uint32_t>(v) & 0x7FFFFu;
-        const uint32_t mh = static_cast<uint32_t>(v >> 19) & 0x7FFFFu;
-        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
-        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
-        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
-        if (lane == 0) {
-            s.sWarpAcc[warp][d] = sc;
-            s.sWarpAcc[warp][DT + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
-        }
-    }
-    __syncthreads();
     if (tid < 2 * D) {
-        const int j = tid < D ? tid : DT + (tid - D);
+        const int j = tid < D ? core_off + tid : mem_off + (tid - D);
         unsigned long long tot = 0;
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) tot += s.sWarpAcc[w][j];
+        for (int w = 0; w < WARPS; ++w) tot += wacc[w * wstride + j];
         if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
         __threadfence();  // only the threads that published sums need to order them before the ticket
     }
     __syncthreads();
     if (tid == 0) {
         const unsigned int ticket = atomicAdd(&ep.ticket, 1u);
-        s.sLast = (ticket == gridDim.x - 1);
+        *sLast = (ticket == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s.sLast) return;
+    if (!*sLast) return;
     __threadfence();
     const bool fin = (flags & kFlagFinalize) != 0;
     const bool commit = fin && (flags & kFlagCommit);
@@ -185,12 +181,39 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
             st->free_core[tid] = cc;
             st->free_mem[tid] = cm;
             st->oversub[tid] |= over;
-            s.sFc[tid] = cc;
-            s.sFm[tid] = cm;
+            sFc[tid] = cc;
+            sFm[tid] = cm;
         }
     }
-    if (commit) resort_table_cta(st, D, s.sFc, s.sFm, s.sPosDev, tid);
+    if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
     if (tid == 0) ep.ticket = 0u;
+}
+
+// Demand sums -> global running sums -> (last CTA) delta / table' publication.
+template <int DT, int THREADS>
+__device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
+                                                  long long* __restrict__ delta_out,
+                                                  int32_t* __restrict__ table_out, int flags, int slot) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    __syncwarp();
+    for (int d = 0; d < D; ++d) {
+        const unsigned long long v = s.hist[warp][d + 1][lane];
+        const uint32_t c = static_cast<uint32_t>(v >> kAccShift);
+        const uint32_t ml = static_cast<uint32_t>(v) & 0x7FFFFu;
+        const uint32_t mh = static_cast<uint32_t>(v >> 19) & 0x7FFFFu;
+        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
+        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
+        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
+        if (lane == 0) {
+            s.sWarpAcc[warp][d] = sc;
+            s.sWarpAcc[warp][DT + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
+        }
+    }
+    __syncthreads();
+    epilogue_publish<THREADS / 32>(&s.sWarpAcc[0][0], 2 * DT, 0, DT, s.sFc, s.sFm, s.sPosDev, &s.sLast, st, D, delta_out,
+                                   table_out, flags, slot);
 }
 
 template <int DT, int THREADS>
@@ -232,6 +255,7 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         const uint4 k4 = *reinterpret_cast<const uint4*>(&st->sorted_k[j]);
         K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
     }
+    const uint32_t gx = st->cand_xor, gm = st->cand_mask;
     // warp-private tile of the position -> device map: only a warp-level barrier
     int32_t* tile = s.sDevTile[warp];
     for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
@@ -239,7 +263,7 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     __syncwarp();
 
     auto decide = [&](int32_t core, int32_t mem) -> int32_t {
-        const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem));
+        const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem), gx, gm);
         const int32_t idx = tile[best];  // best <= DT; tile[DT] = -1
         hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
         return idx;
@@ -337,6 +361,191 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
     snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot);
+}
+
+// =============================================================================
+// Lookup-table scan for large D (EGPU_VARIANT_LUT; AUTO picks it for D > 16)
+// =============================================================================
+//
+// The register-resident scan above costs 3.5 instructions per (request, device) pair:
+// fine for D = 8 (HBM-bound), ALU-bound by 4x at D = 64.  The lookup form needs three
+// shared-memory reads and ~20 instructions per request whatever D is.
+
+// Builds DevLut from the sorted view in DevState.  One CTA; runs after every table change.
+__global__ void __launch_bounds__(256)
+lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
+    __shared__ uint32_t sFm[kMaxD], sFcs[kMaxD], sV[kMaxD];
+    __shared__ int sFirst[kMaxD], sRidx[kMaxD], sNv;
+    const int tid = threadIdx.x;
+    const int D = st->D;
+    if (tid < kMaxD) {
+        const uint32_t k = tid < D ? st->sorted_k[tid] : 0u;
+        sFm[tid] = (k >> 5) & 0x3FFFFu;
+        sFcs[tid] = (k >> 24) & 0x7Fu;
+        sV[tid] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (tid < D) {  // first occurrence of its fm value?
+        int first = 1;
+        for (int k = 0; k < tid; ++k) first &= (sFm[k] != sFm[tid]);
+        sFirst[tid] = first;
+    }
+    __syncthreads();
+    if (tid < D) {  // ridx = number of distinct values below mine
+        int r = 0;
+        for (int k = 0; k < D; ++k) r += (sFirst[k] && sFm[k] < sFm[tid]);
+        sRidx[tid] = r;
+        sV[r] = sFm[tid];
+    }
+    if (tid == 0) {
+        int nv = 0;
+        for (int k = 0; k < D; ++k) nv += sFirst[k];
+        sNv = nv;
+        lut->nv = nv;
+    }
+    __syncthreads();
+    const int nv = sNv;
+    if (tid < kMaxD) lut->v[tid] = sV[tid];
+    if (tid < 128) {  // start[c] = first sorted position with fc >= c
+        int n = 0;
+        for (int k = 0; k < D; ++k) n += (sFcs[k] < static_cast<uint32_t>(tid));
+        lut->start[tid] = static_cast<uint8_t>(n);
+    }
+    if (tid < kLutStride) {  // column r of a[][]: walk the suffixes from the back
+        const int r = tid;
+        uint8_t cur = 0xFF;
+        for (int srow = kMaxD; srow >= 0; --srow) {
+            if (srow < D && sRidx[srow] >= r) cur = static_cast<uint8_t>(st->sorted_dev[srow]);
+            if (srow > D) cur = 0xFF;
+            lut->a[srow * kLutStride + r] = cur;
+        }
+    }
+    for (int b = tid; b < kLutBuckets; b += blockDim.x) {
+        const uint32_t lo_v = static_cast<uint32_t>(b) << 6, hi_v = lo_v + 64u;
+        int lo = 0, hi = 0;
+        for (int k = 0; k < nv; ++k) {
+            lo += (sV[k] < lo_v);
+            hi += (sV[k] < hi_v);
+        }
+        lut->bucket[b] = static_cast<uint16_t>(lo | ((hi - lo) << 8));
+    }
+}
+
+template <int THREADS>
+struct LutSmem {
+    DevLut lut;
+    // one accumulator row per WARP (not per lane): lanes choosing the same device are
+    // grouped with match.any, their requests summed with redux over the group mask, and
+    // the group leader alone updates the row - no conflicts, 1 KB per warp, full occupancy
+    unsigned long long wacc[THREADS / 32][2 * (kMaxD + 1)];  // [0..64] core, [65..129] mem; index idx + 1
+    int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    int sLast;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
+                   const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
+                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot,
+                   const DevLut* __restrict__ glut) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& sm = *reinterpret_cast<LutSmem<THREADS>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool late = (flags & kFlagLateWait) != 0;
+    if (!late) pdl_wait();
+    pdl_trigger();
+
+    const long long nvec = R >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
+    bool has0 = v < nvec, has1 = (v + stride) < nvec;
+    if (has0) {
+        c0 = ld_stream_v4(req_core + 4 * v);
+        m0 = ld_stream_v4(req_mem + 4 * v);
+    }
+    if (has1) {
+        c1 = ld_stream_v4(req_core + 4 * (v + stride));
+        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
+    }
+    // shared-memory tile of the lookup tables (12.8 KB, L2-resident source)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(glut);
+        uint4* dst = reinterpret_cast<uint4*>(&sm.lut);
+        for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
+    }
+    const int D = st->D;
+    unsigned long long* wacc = sm.wacc[warp];
+    for (int i = lane; i < 2 * (kMaxD + 1); i += 32) wacc[i] = 0ull;
+    __syncthreads();
+    const DevLut& L = sm.lut;
+
+    // `active`: lanes of the warp executing this call together (uniform per call site)
+    auto decide = [&](int32_t core, int32_t mem, unsigned active) -> int32_t {
+        const uint32_t c = min(static_cast<uint32_t>(core), 127u);
+        const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
+        const uint32_t srow = L.start[c];
+        const uint32_t e = L.bucket[m >> 6];
+        uint32_t rank = e & 0xffu;
+        for (uint32_t i = 0, n = e >> 8; i < n; ++i) rank += (L.v[(e & 0xffu) + i] < m);
+        const int32_t idx = static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
+        // demand sums: group the lanes by chosen device
+        const unsigned peers = __match_any_sync(active, idx);
+        const uint32_t sc = __reduce_add_sync(peers, c);
+        const uint32_t sm_ = __reduce_add_sync(peers, m);
+        if (lane == __ffs(peers) - 1) {
+            wacc[idx + 1] += sc;
+            wacc[kMaxD + 1 + idx + 1] += sm_;
+        }
+        __syncwarp(active);
+        return idx;
+    };
+    while (has0) {
+        const long long vn = v + 2 * stride;
+        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
+        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
+        if (nhas0) {
+            nc0 = ld_stream_v4(req_core + 4 * vn);
+            nm0 = ld_stream_v4(req_mem + 4 * vn);
+        }
+        if (nhas1) {
+            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
+            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
+        }
+        {
+            const unsigned act = __activemask();
+            int4 r;
+            r.x = decide(c0.x, m0.x, act);
+            r.y = decide(c0.y, m0.y, act);
+            r.z = decide(c0.z, m0.z, act);
+            r.w = decide(c0.w, m0.w, act);
+            st_stream_v4(out_idx + 4 * v, r);
+        }
+        if (has1) {
+            const unsigned act = __activemask();
+            int4 r;
+            r.x = decide(c1.x, m1.x, act);
+            r.y = decide(c1.y, m1.y, act);
+            r.z = decide(c1.z, m1.z, act);
+            r.w = decide(c1.w, m1.w, act);
+            st_stream_v4(out_idx + 4 * (v + stride), r);
+        }
+        v = vn;
+        has0 = nhas0;
+        has1 = nhas1;
+        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
+    }
+    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
+        const long long r = (nvec << 2) + tid;
+        const unsigned act = __activemask();
+        out_idx[r] = decide(req_core[r], req_mem[r], act);
+    }
+    __syncthreads();
+    epilogue_publish<THREADS / 32>(&sm.wacc[0][0], 2 * (kMaxD + 1), 1, kMaxD + 2, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
+                                   delta_out, table_out, flags, slot);
+    if (late) pdl_wait();
 }
 
 // Multi-GPU step 2: table' = table - sum over ranks of their demand vectors.
@@ -514,8 +723,12 @@ using namespace egpu;
 
 using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int, int);
 
+using LutKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int, int,
+                           const egpu::DevLut*);
+
 struct SnapLaunch {
     SnapKernel fn = nullptr;
+    LutKernel lut_fn = nullptr;  // set instead of fn for the lookup-table scan
     int threads = 0;
     size_t smem = 0;
     int ctas_per_sm = 0;  // 0 = not configured yet on this context
@@ -523,7 +736,9 @@ struct SnapLaunch {
 
 struct egpu_ctx {
     std::mutex mu;
-    SnapLaunch snap[2][4];
+    SnapLaunch snap[3][4];            // [sorted, grid, lut][D bucket]
+    DevLut* d_lut = nullptr;
+    bool lut_dirty = true;            // table changed since the lookup tables were built
     int dev = -1;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -593,7 +808,7 @@ SnapLaunch pick_launch(int D, bool grid_variant) {
 void fill_sorted(DevState& h) {
     const int D = h.D;
     for (int j = 0; j < kMaxD; ++j) {
-        h.sorted_k[j] = 0u;
+        h.sorted_k[j] = kPadWord;
         h.sorted_dev[j] = -1;
     }
     unsigned long long packed = ~0ull;
@@ -604,7 +819,7 @@ void fill_sorted(DevState& h) {
             const uint32_t other = (static_cast<uint32_t>(h.free_core[k]) << 24) | (static_cast<uint32_t>(h.free_mem[k]) << 6) | k;
             pos += other < mine;
         }
-        h.sorted_k[pos] = pack_table_word(h.free_core[d], h.free_mem[d]);
+        h.sorted_k[pos] = pack_table_word(h.free_core[d], h.free_mem[d]) | (static_cast<uint32_t>(pos) & 31u);
         h.sorted_dev[pos] = d;
         if (pos < 8) packed = (packed & ~(0xffull << (8 * pos))) | (static_cast<unsigned long long>(d) << (8 * pos));
     }
@@ -617,14 +832,30 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
                     long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
                     int rpt_hint = 0) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
+    const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
-    SnapLaunch& l = ctx->snap[grid_variant ? 1 : 0][bucket];
+    SnapLaunch& l = ctx->snap[grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
     if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
-        l = pick_launch(ctx->D, grid_variant);
-        EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
         int per_sm = 0;
-        EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
+        if (lut_variant) {
+            l.lut_fn = bestfit_lut_kernel<256>;
+            l.threads = 256;
+            l.smem = sizeof(LutSmem<256>);
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
+        } else {
+            l = pick_launch(ctx->D, grid_variant);
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
+        }
         l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    }
+    if (lut_variant && ctx->lut_dirty) {  // refresh the lookup tables on the launching stream
+        lut_build_kernel<<<1, 256, 0, s>>>(ctx->d_state, ctx->d_lut);
+        EGPU_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        ctx->lut_dirty = false;
+        ctx->prev_is_scan = false;
     }
     int flags = (finalize ? kFlagFinalize : 0) | ((user_flags & EGPU_F_COMMIT) ? kFlagCommit : 0);
     // Programmatic dependent launch.  Every scan carries the PDL attribute, so the
@@ -660,7 +891,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // launches, fewer atomics and leaves room for the neighbours — measured best on
     // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
-    int rpt = ((user_flags & EGPU_F_INPUTS_READY) && ctx->D <= 16) ? 48 : 8;
+    int rpt = ((user_flags & EGPU_F_INPUTS_READY) && (ctx->D <= 16 || lut_variant)) ? 48 : 8;
     if (rpt_hint > 0) rpt = rpt_hint;
     if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
     if (grid_variant) rpt = 4;
@@ -685,8 +916,13 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
-                                      d_delta, d_table_out, flags, slot));
+    if (lut_variant)
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.lut_fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
+                                          d_delta, d_table_out, flags, slot, static_cast<const DevLut*>(ctx->d_lut)));
+    else
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
+                                          d_delta, d_table_out, flags, slot));
+    if (flags & kFlagCommit) ctx->lut_dirty = true;
     ctx->launches += 1;
     ctx->seq += 1;
     for (int k = 0; k < 3; ++k) ctx->group_out[3 * ctx->group_len + k] = mine[k];
@@ -773,6 +1009,7 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         EGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_state, sizeof(DevState)));
         EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_state, 0, sizeof(DevState), ctx->stream));
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(DevLut)));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_delta, sizeof(long long) * 2 * kMaxD));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_table_out, sizeof(int32_t) * 3 * kMaxD));
         EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_delta, sizeof(long long) * 2 * kMaxD));
@@ -798,6 +1035,7 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     cudaFree(ctx->d_state);
+    cudaFree(ctx->d_lut);
     cudaFree(ctx->d_req_core);
     cudaFree(ctx->d_req_mem);
     cudaFree(ctx->d_idx);
@@ -819,7 +1057,7 @@ int64_t egpu_launch_count(egpu_ctx* ctx) {
 }
 
 int egpu_set_variant(egpu_ctx* ctx, int variant) {
-    if (!ctx || variant < EGPU_VARIANT_AUTO || variant > EGPU_VARIANT_SORTED) return EGPU_ERR_INVALID;
+    if (!ctx || variant < EGPU_VARIANT_AUTO || variant > EGPU_VARIANT_LUT) return EGPU_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     ctx->variant = variant;
     return EGPU_OK;
@@ -838,13 +1076,17 @@ int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_
     std::memcpy(h.free_core, free_core, sizeof(int32_t) * D);
     std::memcpy(h.free_mem, free_mem, sizeof(int32_t) * D);
     h.D = D;
+    h.cand_xor = kGuards;
+    h.cand_mask = kCandMask;
     fill_sorted(h);
     // pageable source: the copy is staged before the call returns
-    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    // only the table part: the epilogue slots that follow stay as the device left them
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, offsetof(DevState, epi), cudaMemcpyHostToDevice, ctx->stream));
     EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->D = D;
     ctx->has_table = true;
     ctx->prev_is_scan = false;
+    ctx->lut_dirty = true;
     return EGPU_OK;
 }
 
@@ -947,6 +1189,7 @@ int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G, i
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     ctx->prev_is_scan = false;
+    if (commit) ctx->lut_dirty = true;
     apply_deltas_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, reinterpret_cast<const long long*>(d_deltas), G,
                                             d_table_out, commit);
     EGPU_CUDA(ctx, cudaGetLastError());
@@ -1004,6 +1247,7 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
         ctx->prev_is_scan = false;
+        ctx->lut_dirty = true;
         replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
         EGPU_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;

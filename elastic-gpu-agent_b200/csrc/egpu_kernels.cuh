@@ -20,17 +20,24 @@ constexpr int kCoreMax = 100;
 constexpr int kMemMax = (1 << 18) - 1;
 
 // --- packed compare word (internal; the spec's key is (lc, lm, d)) -----------
-//   bit 26      guard C (1)
-//   bits 19..25 free_core          (7 bits, <= 100)
-//   bit 18      guard M (1)
-//   bits 0..17  free_mem           (18 bits)
-// K - Q with Q = core << 19 | mem keeps both guards iff core <= free_core and
-// mem <= free_mem (each field borrows from its own guard only, because
-// |difference| < field range).  One subtract tests both dimensions.
-constexpr uint32_t kGuardC = 1u << 26;
-constexpr uint32_t kGuardM = 1u << 18;
+//   bit 31      guard C (1)
+//   bits 24..30 free_core          (7 bits, <= 100)
+//   bit 23      guard M (1)
+//   bits 5..22  free_mem           (18 bits)
+//   bits 0..4   sorted position mod 32
+// K - Q with Q = core << 24 | mem << 5 keeps both guards iff core <= free_core and
+// mem <= free_mem: each field borrows from its own guard only (|difference| < field
+// range), and Q's low five bits are zero, so the position rides through the subtract.
+// One subtract tests both dimensions; (t ^ G) & (G | 31) is then the position when the
+// row is feasible and a value >= 2^23 when it is not - ready for an unsigned min.
+constexpr uint32_t kGuardC = 1u << 31;
+constexpr uint32_t kGuardM = 1u << 23;
 constexpr uint32_t kGuards = kGuardC | kGuardM;
-constexpr uint32_t kQInvalid = 127u << 19;  // core 127 > any free_core: infeasible everywhere
+constexpr uint32_t kCandMask = kGuards | 31u;
+constexpr uint32_t kNoCand = 32u;  // "no feasible row" among 32 positions
+// Rows past D: guard C alone.  2^31 - Q keeps bit 31 only for Q = 0, and then guard M is
+// missing; any other Q clears bit 31.  Never feasible, whatever the request.
+constexpr uint32_t kPadWord = kGuardC;
 
 // flags of the snapshot kernels
 constexpr int kFlagFinalize = 1;  // last CTA publishes delta / table'
@@ -48,11 +55,14 @@ struct DevState {
     int32_t free_mem[kMaxD];
     int32_t oversub[kMaxD];
     // derived, refreshed whenever the table changes: rows sorted by (fc, fm, d)
-    uint32_t sorted_k[kMaxD];             // packed compare words, 0 past D
+    uint32_t sorted_k[kMaxD];             // packed compare words, kPadWord past D
     int32_t sorted_dev[kMaxD];            // sorted position -> device, -1 past D
     unsigned long long dev_packed;        // D <= 8: byte j = device at position j (0xff = none)
     int32_t D;
-    int32_t pad_[1];
+    uint32_t pad_;
+    // kGuards and kCandMask, read at run time: as compile-time constants ptxas emits two
+    // LOP3 with one immediate each; from registers (t ^ G) & M is a single 3-input LOP3
+    uint32_t cand_xor, cand_mask, pad2_[2];
     // Epilogue state is per launch (slot = launch sequence mod kEpiSlots): several scans may
     // be in flight at once and each needs its own running sums and arrival ticket.
     struct EpiSlot {
@@ -64,17 +74,35 @@ struct DevState {
 constexpr int kEpiSlots = 32;      // ring used by pipelined launches; slot 32 = accumulate-only launches
 constexpr int kPipeGroupMax = 24;  // at most this many launches between two fully ordered ones
 
+// Lookup form of the sorted table, for large D.  With rows sorted by
+// (fc, fm, d) the best fit of (c, m) is the first position j >= start[c] whose
+// fm_j >= m.  Let V be the distinct fm values in ascending order and rank(m) = #V < m;
+// then fm_j >= m  <=>  ridx_j >= rank(m)  (ridx_j = #V < fm_j), so the answer is a pure
+// table lookup  a[start[c]][rank(m)]  (device id, 0xFF = none).  rank(m) comes from a
+// bucket table over m >> 6: entry = (#V below the bucket) | (#V inside it) << 8.
+constexpr int kLutStride = kMaxD + 1;
+constexpr int kLutBuckets = (1 << 18 >> 6) + 1;  // last bucket: mem clamped to 2^18 = out of domain
+struct DevLut {
+    uint16_t bucket[kLutBuckets + 7];
+    uint8_t a[kLutStride * kLutStride + 15];
+    uint32_t v[kMaxD];
+    uint8_t start[128];
+    int32_t nv;
+    int32_t pad_[3];
+};
+static_assert(sizeof(DevLut) % 16 == 0, "DevLut is copied with 128-bit loads");
+
 __host__ __device__ __forceinline__ uint32_t pack_table_word(int32_t fc, int32_t fm) {
-    return kGuardC | (static_cast<uint32_t>(fc) << 19) | kGuardM | static_cast<uint32_t>(fm);
+    return kGuardC | (static_cast<uint32_t>(fc) << 24) | kGuardM | (static_cast<uint32_t>(fm) << 5);
 }
 
 __device__ __forceinline__ uint32_t pack_request_word(int32_t core, int32_t mem) {
     // out-of-domain values clamp to "infeasible everywhere": a negative int is a huge
     // unsigned; core 127 exceeds every free_core (<= 100); mem 2^18 clears guard M of
-    // every table word (free_mem + 2^18 - 2^18 < 2^18) without touching the core field
+    // every table word (2^18 + free_mem - 2^18 < 2^18) without touching the core field
     const uint32_t c = min(static_cast<uint32_t>(core), 127u);
     const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
-    return (c << 19) + m;
+    return (c << 24) + (m << 5);
 }
 
 // streaming 128-bit accesses: read-once / write-once data stays out of L1

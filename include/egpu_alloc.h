@@ -90,9 +90,10 @@ extern "C" {
                                     launch's tail (programmatic dependent launch) */
 
 /* kernel variants for the snapshot scan (egpu_set_variant) */
-#define EGPU_VARIANT_AUTO    0   /* library picks per D */
+#define EGPU_VARIANT_AUTO    0   /* SORTED for D <= 16, LUT above */
 #define EGPU_VARIANT_GRID    1   /* direct (device x request) score grid, min over packed keys */
-#define EGPU_VARIANT_SORTED  2   /* first feasible device in (core, mem, d)-sorted order */
+#define EGPU_VARIANT_SORTED  2   /* first feasible device in (core, mem, d)-sorted order, table in registers */
+#define EGPU_VARIANT_LUT     3   /* same order, answered by shared-memory lookup tables (large D) */
 
 typedef struct egpu_ctx egpu_ctx;
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 KAT = json.load(open(os.path.join(HERE, "golden", "bestfit_kat.json")))
 SYN = json.load(open(os.path.join(HERE, "golden", "bestfit_synth.json")))
-VARIANTS = [1, 2]  # EGPU_VARIANT_GRID, EGPU_VARIANT_SORTED
+VARIANTS = [1, 2, 3]  # EGPU_VARIANT_GRID, EGPU_VARIANT_SORTED, EGPU_VARIANT_LUT
 
 
 def digest(a):
@@ -120,7 +120,7 @@ def test_zero_copy_pinned_buffers(D, dist, alloc, oracle_c, egpu):
         n0 = alloc.launch_count
         alloc.bestfit_raw(pc.ctypes.data + 4 * off, pm.ctypes.data + 4 * off, R, pi.ctypes.data + 4 * off,
                           dc.ctypes.data, dm.ctypes.data)
-        assert alloc.launch_count == n0 + 1
+        assert alloc.launch_count in (n0 + 1, n0 + 2)  # one scan (+ one lookup-table build after set_table)
         assert np.array_equal(pi[off:off + R], o_idx)
         assert (pi[:off] == -9).all() and (pi[off + R:] == -9).all()
         assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
@@ -335,7 +335,8 @@ def test_full_size_properties_64mi(alloc, egpu):
         alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, s)
         torch.cuda.synchronize()
         outs.append((idx, delta))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
     idx, delta = outs[1]
     assert bool((idx[15::16] == -1).all())
     fc = torch.tensor(w["free_core"], device="cuda")
