@@ -431,28 +431,33 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
     }
 }
 
-template <int THREADS>
+// Demand sums of the lookup scan: lane-private like SnapSmem::hist, but SHARE lanes share
+// one accumulator (SHARE = 1, 2 or 4) and take turns, SHARE phases per update.  D = 64
+// with SHARE = 1 costs 16.6 KB per warp, which caps an SM at 8-12 warps; sharing trades
+// a few issue slots (the scan is nowhere near ALU-bound) for occupancy.
+template <int THREADS, int SHARE>
 struct LutSmem {
     DevLut lut;
-    // one accumulator row per WARP (not per lane): lanes choosing the same device are
-    // grouped with match.any, their requests summed with redux over the group mask, and
-    // the group leader alone updates the row - no conflicts, 1 KB per warp, full occupancy
-    unsigned long long wacc[THREADS / 32][2 * (kMaxD + 1)];  // [0..64] core, [65..129] mem; index idx + 1
+    unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
     int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     int sLast;
+    unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];
 };
 
-template <int THREADS>
+template <int THREADS, int SHARE>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot,
                    const DevLut* __restrict__ glut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& sm = *reinterpret_cast<LutSmem<THREADS>*>(smem_raw);
+    auto& sm = *reinterpret_cast<LutSmem<THREADS, SHARE>*>(smem_raw);
+    constexpr int LW = 32 / SHARE;  // accumulator columns per warp
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int col = lane & (LW - 1);
+    const int phase = lane / LW;
     const bool late = (flags & kFlagLateWait) != 0;
     if (!late) pdl_wait();
     pdl_trigger();
@@ -477,32 +482,51 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
     }
     const int D = st->D;
-    unsigned long long* wacc = sm.wacc[warp];
-    for (int i = lane; i < 2 * (kMaxD + 1); i += 32) wacc[i] = 0ull;
+    if (phase == 0) {
+#pragma unroll 1
+        for (int d = 0; d <= kMaxD; ++d) sm.hist[warp][d][col] = 0ull;
+    }
     __syncthreads();
     const DevLut& L = sm.lut;
 
-    // `active`: lanes of the warp executing this call together (uniform per call site)
-    auto decide = [&](int32_t core, int32_t mem, unsigned active) -> int32_t {
+    // lookups for one request: no data-dependent loop on the common path
+    auto lookup = [&](int32_t core, int32_t mem) -> int32_t {
         const uint32_t c = min(static_cast<uint32_t>(core), 127u);
         const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
         const uint32_t srow = L.start[c];
         const uint32_t e = L.bucket[m >> 6];
-        uint32_t rank = e & 0xffu;
-        for (uint32_t i = 0, n = e >> 8; i < n; ++i) rank += (L.v[(e & 0xffu) + i] < m);
-        const int32_t idx = static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
-        // demand sums: group the lanes by chosen device
-        const unsigned peers = __match_any_sync(active, idx);
-        const uint32_t sc = __reduce_add_sync(peers, c);
-        const uint32_t sm_ = __reduce_add_sync(peers, m);
-        if (lane == __ffs(peers) - 1) {
-            wacc[idx + 1] += sc;
-            wacc[kMaxD + 1 + idx + 1] += sm_;
-        }
-        __syncwarp(active);
-        return idx;
+        const uint32_t lo = e & 0xffu, n = e >> 8;
+        uint32_t rank = lo + ((n != 0u) & (L.v[lo & 63u] < m));
+        for (uint32_t i = 1; i < n; ++i) rank += (L.v[lo + i] < m);  // rare: several distinct fm in one 64 MiB bucket
+        return static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
     };
-    while (has0) {
+    auto accumulate = [&](int32_t idx, int32_t core, int32_t mem) {
+        const unsigned long long val = (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
+                                       static_cast<unsigned long long>(static_cast<uint32_t>(mem));
+        unsigned long long* h = &sm.hist[warp][idx + 1][col];
+        if (SHARE == 1) {
+            *h += val;
+        } else {
+#pragma unroll
+            for (int p = 0; p < SHARE; ++p) {
+                if (phase == p) *h += val;
+                __syncwarp();
+            }
+        }
+    };
+    auto decide4 = [&](const int4& c, const int4& m) -> int4 {
+        int4 r;
+        r.x = lookup(c.x, m.x);
+        r.y = lookup(c.y, m.y);
+        r.z = lookup(c.z, m.z);
+        r.w = lookup(c.w, m.w);
+        accumulate(r.x, c.x, m.x);
+        accumulate(r.y, c.y, m.y);
+        accumulate(r.z, c.z, m.z);
+        accumulate(r.w, c.w, m.w);
+        return r;
+    };
+    while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: accumulate() synchronises the warp
         const long long vn = v + 2 * stride;
         const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
         int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
@@ -514,36 +538,43 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
             nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
             nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
         }
-        {
-            const unsigned act = __activemask();
-            int4 r;
-            r.x = decide(c0.x, m0.x, act);
-            r.y = decide(c0.y, m0.y, act);
-            r.z = decide(c0.z, m0.z, act);
-            r.w = decide(c0.w, m0.w, act);
-            st_stream_v4(out_idx + 4 * v, r);
-        }
-        if (has1) {
-            const unsigned act = __activemask();
-            int4 r;
-            r.x = decide(c1.x, m1.x, act);
-            r.y = decide(c1.y, m1.y, act);
-            r.z = decide(c1.z, m1.z, act);
-            r.w = decide(c1.w, m1.w, act);
-            st_stream_v4(out_idx + 4 * (v + stride), r);
-        }
+        // lanes past the end carry core = mem = -1: infeasible, lands in the dummy row
+        if (!has0) { c0 = make_int4(-1, -1, -1, -1); m0 = c0; }
+        if (!has1) { c1 = make_int4(-1, -1, -1, -1); m1 = c1; }
+        const int4 r0 = decide4(c0, m0);
+        const int4 r1 = decide4(c1, m1);
+        if (has0) st_stream_v4(out_idx + 4 * v, r0);
+        if (has1) st_stream_v4(out_idx + 4 * (v + stride), r1);
         v = vn;
         has0 = nhas0;
         has1 = nhas1;
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
-    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
-        const long long r = (nvec << 2) + tid;
-        const unsigned act = __activemask();
-        out_idx[r] = decide(req_core[r], req_mem[r], act);
+    if (blockIdx.x == 0 && warp == 0) {  // ragged tail: R % 4 rows; whole warp takes part in accumulate()
+        const bool mine = lane < static_cast<int>(R & 3);
+        const long long r = (nvec << 2) + lane;
+        const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
+        const int32_t idx = lookup(c, m);
+        accumulate(idx, c, m);
+        if (mine) out_idx[r] = idx;
+    }
+    // warp sums -> sWarpAcc (same layout as the register scan's epilogue)
+    __syncwarp();
+    for (int d = 0; d < D; ++d) {
+        const unsigned long long hv = phase == 0 ? sm.hist[warp][d + 1][col] : 0ull;
+        const uint32_t c = static_cast<uint32_t>(hv >> kAccShift);
+        const uint32_t ml = static_cast<uint32_t>(hv) & 0x7FFFFu;
+        const uint32_t mh = static_cast<uint32_t>(hv >> 19) & 0x7FFFFu;
+        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
+        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
+        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
+        if (lane == 0) {
+            sm.sWarpAcc[warp][d] = sc;
+            sm.sWarpAcc[warp][kMaxD + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
+        }
     }
     __syncthreads();
-    epilogue_publish<THREADS / 32>(&sm.wacc[0][0], 2 * (kMaxD + 1), 1, kMaxD + 2, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
+    epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
                                    delta_out, table_out, flags, slot);
     if (late) pdl_wait();
 }
@@ -770,6 +801,7 @@ struct egpu_ctx {
     int pipe_group = 16;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
+    int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
     char last_err[256] = {0};
 };
 
@@ -838,9 +870,12 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
         int per_sm = 0;
         if (lut_variant) {
-            l.lut_fn = bestfit_lut_kernel<256>;
-            l.threads = 256;
-            l.smem = sizeof(LutSmem<256>);
+            const int share = ctx->lut_share;
+            l.lut_fn = share == 1 ? bestfit_lut_kernel<128, 1> : share == 2 ? bestfit_lut_kernel<128, 2>
+                       : share == 4 ? bestfit_lut_kernel<128, 4> : bestfit_lut_kernel<128, 8>;
+            l.threads = 128;
+            l.smem = share == 1 ? sizeof(LutSmem<128, 1>) : share == 2 ? sizeof(LutSmem<128, 2>)
+                     : share == 4 ? sizeof(LutSmem<128, 4>) : sizeof(LutSmem<128, 8>);
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
@@ -891,7 +926,9 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // launches, fewer atomics and leaves room for the neighbours — measured best on
     // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
-    int rpt = ((user_flags & EGPU_F_INPUTS_READY) && (ctx->D <= 16 || lut_variant)) ? 48 : 8;
+    int rpt = 8;
+    if (user_flags & EGPU_F_INPUTS_READY) rpt = lut_variant ? 96 : (ctx->D <= 16 ? 48 : 8);  // measured, scripts/tune_*.sh
+    else if (lut_variant) rpt = 32;  // the lookup scan has a 13 KB per-CTA table tile to amortise
     if (rpt_hint > 0) rpt = rpt_hint;
     if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
     if (grid_variant) rpt = 4;
@@ -1002,6 +1039,10 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         ctx->sm_count = prop.multiProcessorCount;
         if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
+        if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
+            const int v = std::atoi(e);
+            ctx->lut_share = (v == 1 || v == 2 || v == 8) ? v : 4;
+        }
         if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {
             const int g = std::atoi(e);
             ctx->pipe_group = g < 1 ? 1 : (g > kPipeGroupMax ? kPipeGroupMax : g);

@@ -1,0 +1,9 @@
+# LUT-scan tuning sweep (run under gpurun): cfg4 = 64 devices x 1M requests
+run() { env "$@" python bench.py --workload cfg4 --steps 480 --warmup 20 --cpu-budget 0.1 --no-sweep > gpurun_out/b.json 2> gpurun_out/b.err; python - "$*" <<PY
+import json,sys
+try:
+    j=json.load(open("gpurun_out/b.json")); print(sys.argv[1], "us/step", round(1e3*j["ms_per_step"],3), "frac", round(j["roofline"]["frac"],3), "parity", j["parity_vs_oracle"])
+except Exception as ex: print(sys.argv[1], "FAILED", ex, open("gpurun_out/b.err").read()[-800:])
+PY
+}
+for sh in 4 8; do for t in 48 64 96 128 192; do run EGPU_LUT_SHARE=$sh EGPU_ROWS_PER_THREAD=$t; done; done
