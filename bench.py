@@ -42,6 +42,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "alloc_decisions_per_sec"
 UNIT = "decisions/s"
+APPLY_BATCH = 4  # N > 1: one apply launch covers this many steps' demand vectors
 RING = 16  # batches in the rotation: 16 x 12 MB (1M rows) = 192 MB > 126 MB L2
 
 
@@ -176,10 +177,15 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: demand vectors through peer memory fused into the scan (default) or NCCL all-gather")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO would print there
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,11 +231,38 @@ def main():
     table_out = torch.zeros(3 * D, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
+    # N > 1, default: exchange fused into the scan through peer memory (CUDA IPC over NVLink)
+    use_peer = world > 1 and args.exchange == "peer"
+    apply_stream = torch.cuda.Stream() if use_peer else None
+    apply_done = {}
+    step_no = [0]
+    if use_peer:
+        handles = [None] * world
+        dist.all_gather_object(handles, alloc.peer_export())
+        alloc.peer_attach(rank, world, handles)
+        dist.barrier()
+
     def step(i):
         c, m, idx, dl, to = ring[i % nb]
         if world == 1:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), to.data_ptr(), False, sh,
                               inputs_ready=True)
+        elif use_peer:
+            # scans stay back to back on the launching stream (they overlap each other); the
+            # apply kernels run on a second stream and are ordered by DATA: each waits for the
+            # flags of its step.  Every 8 steps the scans wait for the apply of 8 steps ago,
+            # which keeps a rank within the 32 exchange slots.
+            k = step_no[0]
+            step_no[0] += 1
+            if k % 8 == 0 and (k - 8) in apply_done:
+                stream.wait_event(apply_done[k - 8])
+            alloc.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, sh, inputs_ready=True)
+            alloc.apply_peers_dev(k, to.data_ptr(), False, apply_stream.cuda_stream)
+            if k % 8 == 0:
+                ev = torch.cuda.Event()
+                ev.record(apply_stream)
+                apply_done[k] = ev
+                apply_done.pop(k - 16, None)
         else:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, sh)
             dist.all_gather_into_tensor(gathered, delta)
@@ -249,7 +282,7 @@ def main():
         step(i)
     torch.cuda.synchronize()
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = (world == 1 or use_peer) and not args.no_graph
     graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
@@ -258,11 +291,35 @@ def main():
         with torch.cuda.stream(cap):
             csh = cap.cuda_stream
             with torch.cuda.graph(graph, stream=cap):
-                for i in range(args.steps):
-                    c, m, idx, dl, to = ring[i % nb]
-                    alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(),
-                                      to.data_ptr(), False, csh, inputs_ready=True)
+                if use_peer:
+                    # two chains in the graph: scans (programmatic edges between them) and
+                    # apply kernels, coupled every 8 steps; step numbers restart at 0 on
+                    # every replay (the apply kernel consumes the flags, so that is safe)
+                    apply_stream.wait_stream(cap)
+                    done = {}
+                    for k in range(args.steps):
+                        c, m, idx, dl, to = ring[k % nb]
+                        if k % 8 == 0 and (k // 8 - 2) in done:
+                            cap.wait_event(done[k // 8 - 2])  # scans run at most 16 steps ahead of the applies
+                        alloc.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, csh,
+                                                inputs_ready=True)
+                        if k % APPLY_BATCH == APPLY_BATCH - 1 or k == args.steps - 1:
+                            first = k - (k % APPLY_BATCH)
+                            outs = [ring[j % nb][4].data_ptr() for j in range(first, k + 1)]
+                            alloc.apply_peers_multi_dev(first, outs, False, apply_stream.cuda_stream)
+                        if k % 8 == 7:
+                            ev = torch.cuda.Event()
+                            ev.record(apply_stream)
+                            done[k // 8] = ev
+                    cap.wait_stream(apply_stream)
+                else:
+                    for i in range(args.steps):
+                        c, m, idx, dl, to = ring[i % nb]
+                        alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(),
+                                          to.data_ptr(), False, csh, inputs_ready=True)
         stream.wait_stream(cap)
+        if world > 1:
+            dist.barrier()
         graph.replay()  # warm the instantiated graph once
         torch.cuda.synchronize()
 
@@ -275,10 +332,13 @@ def main():
     else:
         for i in range(args.steps):
             step(i)
+    if use_peer and graph is None:
+        stream.wait_stream(apply_stream)  # the timed region ends when the last table' is written
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = (alloc.launch_count - launches0) if graph is None else args.steps
+    launches = (alloc.launch_count - launches0) if graph is None else (
+        args.steps + (args.steps + APPLY_BATCH - 1) // APPLY_BATCH if use_peer else args.steps)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -295,6 +355,24 @@ def main():
             exp, edc, edm, etab = oracle_c.snapshot(w["free_core"], w["free_mem"], rc_h, rm_h, oracle_c.max_threads())
             parity = parity and bool(np.array_equal(ring[b][2].cpu().numpy(), exp))
             parity = parity and bool(np.array_equal(ring[b][3].cpu().numpy(), np.concatenate([edc, edm])))
+            parity = parity and bool(np.array_equal(ring[b][4].cpu().numpy(), etab))
+
+    if rank == 0 and use_peer and R <= (1 << 20):
+        from oracle import oracle_c
+        parity = alloc.peer_last_timeout == 0
+        for b in range(min(nb, 4)):
+            tot_c = np.zeros(D, dtype=np.int64)
+            tot_m = np.zeros(D, dtype=np.int64)
+            for g in range(world):
+                rc_h, rm_h = e.synth.requests(w["dist"], w["seed"], R, first_row=(g * nb + b) * R)
+                exp, edc, edm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc_h, rm_h, oracle_c.max_threads())
+                tot_c += edc
+                tot_m += edm
+                if g == 0:
+                    parity = parity and bool(np.array_equal(ring[b][2].cpu().numpy(), exp))
+                    parity = parity and bool(np.array_equal(ring[b][3].cpu().numpy(), np.concatenate([edc, edm])))
+            from elastic_gpu_agent_b200 import sharding
+            etab = sharding.combine_demands(w["free_core"], w["free_mem"], np.concatenate([tot_c, tot_m])[None, :])
             parity = parity and bool(np.array_equal(ring[b][4].cpu().numpy(), etab))
 
     # ---- end-to-end leg: host buffers through the C ABI -----------------------
@@ -416,7 +494,11 @@ def main():
                        "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
                        "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
                              if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
-                       "launch": "CUDA graph of K scan launches" if graph is not None else "eager launches + NCCL all-gather of demand vectors",
+                       "launch": ("CUDA graph: K scan launches whose last CTA pushes the demand vector to every peer's memory + "
+                                  "one apply launch per 4 steps on a second stream (no NCCL on the data path)") if (graph is not None and use_peer)
+                                 else "CUDA graph of K scan launches" if graph is not None else
+                                 ("eager launches; demand vectors pushed to peer memory by the scan's last CTA, apply kernels on a second stream"
+                                  if use_peer else "eager launches + NCCL all-gather of demand vectors"),
                        "parallelism": f"request rows sharded over {world} GPU(s), table replicated"},
             "e2e": e2e,
             "gpu_launches": int(launches),

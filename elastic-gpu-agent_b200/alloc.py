@@ -153,6 +153,45 @@ class BestFitAllocator:
                                                C.c_void_p(d_core), C.c_void_p(d_mem), C.c_void_p(stream or None))
         self._check(rc, "egpu_synth_requests_dev")
 
+    # -- multi-GPU: peer-memory exchange ----------------------------------------
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.egpu_peer_export(self._h, buf), "egpu_peer_export")
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles: list[bytes]):
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise L.EgpuError(L.ERR_INVALID, "peer_attach")
+        self._check(self._lib.egpu_peer_attach(self._h, int(rank), int(world), C.c_char_p(blob)), "egpu_peer_attach")
+
+    def peer_detach(self):
+        self._check(self._lib.egpu_peer_detach(self._h), "egpu_peer_detach")
+
+    def bestfit_shard_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, step: int, stream: int = 0,
+                          inputs_ready: bool = False):
+        rc = self._lib.egpu_bestfit_batch_shard_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
+                                                    C.c_void_p(d_idx), C.c_void_p(d_delta or None),
+                                                    L.F_INPUTS_READY if inputs_ready else 0, int(step),
+                                                    C.c_void_p(stream or None))
+        self._check(rc, "egpu_bestfit_batch_shard_dev")
+
+    def apply_peers_dev(self, step: int, d_table_out: int = 0, commit: bool = False, stream: int = 0):
+        rc = self._lib.egpu_table_apply_peers_dev(self._h, int(step), C.c_void_p(d_table_out or None),
+                                                  1 if commit else 0, C.c_void_p(stream or None))
+        self._check(rc, "egpu_table_apply_peers_dev")
+
+    def apply_peers_multi_dev(self, first_step: int, d_table_outs: list[int], commit: bool = False, stream: int = 0):
+        n = len(d_table_outs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(p or None) for p in d_table_outs])
+        rc = self._lib.egpu_table_apply_peers_multi_dev(self._h, int(first_step), n, arr, 1 if commit else 0,
+                                                        C.c_void_p(stream or None))
+        self._check(rc, "egpu_table_apply_peers_multi_dev")
+
+    @property
+    def peer_last_timeout(self) -> int:
+        return int(self._lib.egpu_peer_last_timeout(self._h))
+
     # -- sequential mode ------------------------------------------------------
     def replay(self, kind, a, b):
         k, a_, b_ = _i32(kind), _i32(a), _i32(b)

@@ -134,8 +134,11 @@ template <int WARPS>
 __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
                                                  int32_t* sFc, int32_t* sFm, int32_t* sPosDev, int* sLast,
                                                  DevState* st, int D, long long* __restrict__ delta_out,
-                                                 int32_t* __restrict__ table_out, int flags, int slot) {
-    DevState::EpiSlot& ep = st->epi[slot];
+                                                 int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+    // slot_step: bits 0..7 = epilogue slot of this launch; bits 8.. = step + 1 when the demand
+    // vector must also be pushed to the peers' exchange buffers (0 = single GPU)
+    DevState::EpiSlot& ep = st->epi[slot_step & 0xffu];
+    const unsigned long long push = slot_step >> 8;
     const int tid = threadIdx.x;
     if (tid < 2 * D) {
         const int j = tid < D ? core_off + tid : mem_off + (tid - D);
@@ -168,6 +171,16 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
             delta_out[tid] = dc;
             delta_out[D + tid] = dm;
         }
+        if (push) {  // fused exchange: this rank's vector straight into every rank's buffer
+            const int world = st->peer.world, me = st->peer.rank;
+            const int xs = static_cast<int>((push - 1) % kXchgSlots);
+            for (int p = 0; p < world; ++p) {
+                XchgRow& row = st->peer.buf[p]->slot[xs][me];
+                row.delta[tid] = dc;
+                row.delta[D + tid] = dm;
+            }
+            __threadfence_system();
+        }
         if (table_out) {
             table_out[tid] = sat_i32(nc);
             table_out[D + tid] = sat_i32(nm);
@@ -186,6 +199,14 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         }
     }
     if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
+    if (push) {
+        __syncthreads();  // every delta store above is fenced; now raise the flags
+        const int world = st->peer.world, me = st->peer.rank;
+        if (tid < world) {
+            unsigned long long* f = &st->peer.buf[tid]->slot[(push - 1) % kXchgSlots][me].flag;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(push) : "memory");
+        }
+    }
     if (tid == 0) ep.ticket = 0u;
 }
 
@@ -193,7 +214,7 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
 template <int DT, int THREADS>
 __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
                                                   long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags, int slot) {
+                                                  int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -213,14 +234,14 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&s.sWarpAcc[0][0], 2 * DT, 0, DT, s.sFc, s.sFm, s.sPosDev, &s.sLast, st, D, delta_out,
-                                   table_out, flags, slot);
+                                   table_out, flags, slot_step);
 }
 
 template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot) {
+                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -301,7 +322,7 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
     if (late) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
 }
 
@@ -314,7 +335,7 @@ template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                     const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot) {
+                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -360,7 +381,7 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
 }
 
 // =============================================================================
@@ -448,7 +469,7 @@ template <int THREADS, int SHARE>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, int slot,
+                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
                    const DevLut* __restrict__ glut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& sm = *reinterpret_cast<LutSmem<THREADS, SHARE>*>(smem_raw);
@@ -575,7 +596,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
-                                   delta_out, table_out, flags, slot);
+                                   delta_out, table_out, flags, slot_step);
     if (late) pdl_wait();
 }
 
@@ -611,6 +632,85 @@ apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ del
         }
     }
     if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, d);
+}
+
+// Multi-GPU step 2, peer-memory form: wait until every rank's demand vector of `step` has
+// landed in THIS rank's exchange buffer, then apply their sum.  One CTA.  The spin gives up
+// after ~2 s (a rank died): DevState::peer_timeout records it and the table is left alone.
+struct ApplyOuts {
+    int32_t* table_out[8];
+};
+
+__global__ void __launch_bounds__(kMaxD)
+apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus1, int nsteps, ApplyOuts outs, int commit) {
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    __shared__ int sOk;
+    const int D = st->D;
+    const int d = threadIdx.x;
+    const int world = st->peer.world, me = st->peer.rank;
+    // running table across the steps of this launch (only installed when commit is set)
+    long long cur_c = d < D ? st->free_core[d] : 0, cur_m = d < D ? st->free_mem[d] : 0;
+    int32_t sticky = 0;
+    for (int k = 0; k < nsteps; ++k) {
+        const unsigned long long step_plus1 = first_step_plus1 + k;
+        XchgRow* rows = st->peer.buf[me]->slot[(step_plus1 - 1) % kXchgSlots];
+        if (d == 0) sOk = 1;
+        __syncthreads();
+        if (d < world) {
+            unsigned long long f = 0;
+            const long long t0 = clock64();
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[d].flag) : "memory");
+                if (f == step_plus1) break;
+                if (clock64() - t0 > 4000000000ll) {
+                    sOk = 0;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (!sOk) {
+            if (d == 0) st->peer_timeout = step_plus1;
+            return;
+        }
+        long long dc = 0, dm = 0;
+        if (d < D) {
+            for (int g = 0; g < world; ++g) {
+                dc += rows[g].delta[d];
+                dm += rows[g].delta[D + d];
+            }
+        }
+        __syncthreads();
+        // consume the flags: a replayed CUDA graph pushes the same step numbers again, and a
+        // stale flag must not look like the new one.  (The slot is not written again before
+        // this rank has applied 16 more steps, see the header.)
+        if (d < world) rows[d].flag = 0ull;
+        if (d < D) {
+            const long long nc = cur_c - dc, nm = cur_m - dm;
+            const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
+            if (outs.table_out[k]) {
+                outs.table_out[k][d] = sat_i32(nc);
+                outs.table_out[k][D + d] = sat_i32(nm);
+                outs.table_out[k][2 * D + d] = over;
+            }
+            if (commit) {  // the next step of this launch is applied on top of this one
+                cur_c = nc < 0 ? 0 : nc;
+                cur_m = nm < 0 ? 0 : nm;
+                sticky |= over;
+            }
+        }
+    }
+    if (commit) {
+        if (d < D) {
+            st->free_core[d] = static_cast<int32_t>(cur_c);
+            st->free_mem[d] = static_cast<int32_t>(cur_m);
+            st->oversub[d] |= sticky;
+            sFc[d] = static_cast<int32_t>(cur_c);
+            sFm[d] = static_cast<int32_t>(cur_m);
+        }
+        resort_table_cta(st, D, sFc, sFm, sPosDev, d);
+    }
 }
 
 // =============================================================================
@@ -752,10 +852,11 @@ replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const
 // =============================================================================
 using namespace egpu;
 
-using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int, int);
+using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
+                            unsigned long long);
 
-using LutKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int, int,
-                           const egpu::DevLut*);
+using LutKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
+                           unsigned long long, const egpu::DevLut*);
 
 struct SnapLaunch {
     SnapKernel fn = nullptr;
@@ -769,6 +870,10 @@ struct egpu_ctx {
     std::mutex mu;
     SnapLaunch snap[3][4];            // [sorted, grid, lut][D bucket]
     DevLut* d_lut = nullptr;
+    XchgBuf* d_xchg = nullptr;        // this rank's exchange buffer (exported to the peers over CUDA IPC)
+    void* peer_open[kMaxRanks] = {};  // peers' buffers as opened here (nullptr for own rank)
+    int world = 1, rank = 0;
+    bool attached = false;
     bool lut_dirty = true;            // table changed since the lookup tables were built
     int dev = -1;
     int sm_count = 148;
@@ -862,7 +967,7 @@ void fill_sorted(DevState& h) {
 // chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
                     long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
-                    int rpt_hint = 0) {
+                    int rpt_hint = 0, unsigned long long push_step_plus1 = 0) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
@@ -918,7 +1023,8 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             if (mine[k].lo < ctx->group_out[i].hi && ctx->group_out[i].lo < mine[k].hi) pipelined = false;
     if (pipelined) flags |= kFlagLateWait;
     else ctx->group_len = 0;
-    const int slot = finalize ? static_cast<int>(ctx->seq % kEpiSlots) : kEpiSlots;
+    const unsigned long long slot = (finalize ? (ctx->seq % kEpiSlots) : static_cast<unsigned long long>(kEpiSlots)) |
+                                    (push_step_plus1 << 8);
 
     // Grid: one resident wave at most.  A lone launch wants every SM pulling at once
     // (8 rows per thread, one trip); launches of a pipelined stream overlap each
@@ -1051,6 +1157,8 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_state, sizeof(DevState)));
         EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_state, 0, sizeof(DevState), ctx->stream));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(DevLut)));
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_xchg, sizeof(XchgBuf)));
+        EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_xchg, 0, sizeof(XchgBuf), ctx->stream));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_delta, sizeof(long long) * 2 * kMaxD));
         EGPU_CUDA(ctx, cudaMalloc(&ctx->d_table_out, sizeof(int32_t) * 3 * kMaxD));
         EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_delta, sizeof(long long) * 2 * kMaxD));
@@ -1075,6 +1183,9 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
+    cudaFree(ctx->d_xchg);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_req_core);
@@ -1220,6 +1331,115 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
     if (out_delta_core) std::memcpy(out_delta_core, ctx->h_delta, sizeof(int64_t) * D);
     if (out_delta_mem) std::memcpy(out_delta_mem, ctx->h_delta + D, sizeof(int64_t) * D);
     return EGPU_OK;
+}
+
+int egpu_peer_export(egpu_ctx* ctx, void* handle_out) {
+    if (!ctx || !handle_out) return EGPU_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == EGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaIpcMemHandle_t h;
+    EGPU_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_xchg));
+    std::memcpy(handle_out, &h, sizeof h);
+    return EGPU_OK;
+}
+
+int egpu_peer_attach(egpu_ctx* ctx, int rank, int world, const void* handles) {
+    if (!ctx || !handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    PeerCfg cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.world = world;
+    cfg.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            cfg.buf[r] = ctx->d_xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + static_cast<size_t>(r) * sizeof h, sizeof h);
+        void* p = nullptr;
+        EGPU_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_open[r] = p;
+        cfg.buf[r] = static_cast<XchgBuf*>(p);
+    }
+    EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EGPU_CUDA(ctx, cudaMemcpy(reinterpret_cast<char*>(ctx->d_state) + offsetof(DevState, peer), &cfg, sizeof cfg,
+                              cudaMemcpyHostToDevice));
+    ctx->world = world;
+    ctx->rank = rank;
+    ctx->attached = true;
+    return EGPU_OK;
+}
+
+int egpu_peer_detach(egpu_ctx* ctx) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->attached) return EGPU_OK;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    EGPU_CUDA(ctx, cudaDeviceSynchronize());
+    for (int r = 0; r < kMaxRanks; ++r) {
+        if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
+        ctx->peer_open[r] = nullptr;
+    }
+    ctx->attached = false;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return EGPU_OK;
+}
+
+int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
+                                 int32_t* d_out_idx, int64_t* d_delta, int flags, uint64_t step, void* stream) {
+    if (!ctx || R < 0 || (flags & EGPU_F_COMMIT)) return EGPU_ERR_INVALID;  // the commit happens in apply_peers
+    if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (!ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta), nullptr,
+                           flags, true, s, 0, step + 1);
+}
+
+int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nsteps, int32_t* const* d_table_outs,
+                                     int commit, void* stream) {
+    if (!ctx || nsteps < 1 || nsteps > 8) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (!ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (commit) {
+        ctx->lut_dirty = true;
+        ctx->prev_is_scan = false;  // the next scan must see the new table
+    }
+    ApplyOuts outs;
+    for (int k = 0; k < 8; ++k) outs.table_out[k] = (d_table_outs && k < nsteps) ? d_table_outs[k] : nullptr;
+    apply_peers_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, first_step + 1, nsteps, outs, commit);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return EGPU_OK;
+}
+
+int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out, int commit, void* stream) {
+    int32_t* outs[1] = {d_table_out};
+    return egpu_table_apply_peers_multi_dev(ctx, step, 1, outs, commit, stream);
+}
+
+int64_t egpu_peer_last_timeout(egpu_ctx* ctx) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (cudaSetDevice(ctx->dev) != cudaSuccess) return EGPU_ERR_CUDA;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, reinterpret_cast<char*>(ctx->d_state) + offsetof(DevState, peer_timeout), sizeof v,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return EGPU_ERR_CUDA;
+    }
+    return static_cast<int64_t>(v);
 }
 
 int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G, int32_t* d_table_out,

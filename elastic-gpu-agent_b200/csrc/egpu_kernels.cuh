@@ -50,6 +50,24 @@ constexpr int kFlagLateWait = 4;  // programmatic dependent launch: this launch 
 // lane-private demand accumulators pack (core sum << 38 | mem sum) in 64 bits
 constexpr int kAccShift = 38;
 
+// Multi-GPU exchange of demand vectors through peer memory.  Every rank owns
+// one XchgBuf; rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
+// rank's buffer (plain stores over NVLink), followed by flag = s + 1 with release.sys.
+constexpr int kMaxRanks = 8;
+constexpr int kXchgSlots = 32;
+struct XchgRow {
+    long long delta[2 * kMaxD];
+    unsigned long long flag;  // step + 1 once delta[] is complete
+    unsigned long long pad_;
+};
+struct XchgBuf {
+    XchgRow slot[kXchgSlots][kMaxRanks];
+};
+struct PeerCfg {
+    XchgBuf* buf[kMaxRanks];  // device-visible address of every rank's buffer ([rank] = own)
+    int32_t world, rank;
+};
+
 struct DevState {
     int32_t free_core[kMaxD];
     int32_t free_mem[kMaxD];
@@ -63,6 +81,8 @@ struct DevState {
     // kGuards and kCandMask, read at run time: as compile-time constants ptxas emits two
     // LOP3 with one immediate each; from registers (t ^ G) & M is a single 3-input LOP3
     uint32_t cand_xor, cand_mask, pad2_[2];
+    PeerCfg peer;                         // set by egpu_peer_attach
+    unsigned long long peer_timeout;      // step + 1 of the last apply that gave up waiting, else 0
     // Epilogue state is per launch (slot = launch sequence mod kEpiSlots): several scans may
     // be in flight at once and each needs its own running sums and arrival ticket.
     struct EpiSlot {

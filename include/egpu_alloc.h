@@ -161,6 +161,39 @@ int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core,
 int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G,
                                 int32_t* d_table_out, int commit, void* stream);
 
+/* ---- multi-GPU without a collective library on the data path --------------- */
+
+/* One process per GPU.  Each rank exports a CUDA-IPC handle of its exchange buffer
+ * (EGPU_IPC_HANDLE_BYTES bytes), the ranks swap handles by any means (the bench uses
+ * torch.distributed.all_gather_object) and attach: handles = world * 64 bytes, rank
+ * major.  After that a sharded step is two asynchronous calls:
+ *   egpu_bestfit_batch_shard_dev  scans this rank's rows; its last CTA stores the
+ *       rank's demand vector into EVERY rank's exchange buffer over NVLink and raises
+ *       a release flag - the exchange is fused into the scan kernel;
+ *   egpu_table_apply_peers_dev    waits (acquire) until all `world` vectors of `step`
+ *       have landed locally, applies their sum: table' (and commit) as in snapshot mode.
+ * `step` must increase by one per sharded step on every rank; a rank may run at most
+ * 16 steps ahead of its own apply (32 exchange slots).  The scan itself never commits. */
+#define EGPU_IPC_HANDLE_BYTES 64
+#define EGPU_MAX_RANKS 8
+int egpu_peer_export(egpu_ctx* ctx, void* handle_out);
+int egpu_peer_attach(egpu_ctx* ctx, int rank, int world, const void* handles);
+int egpu_peer_detach(egpu_ctx* ctx);
+int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core,
+                                 const int32_t* d_req_mem, int64_t R,
+                                 int32_t* d_out_idx, int64_t* d_delta, int flags,
+                                 uint64_t step, void* stream);
+int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out,
+                               int commit, void* stream);
+/* Same for nsteps (1..8) consecutive steps in one launch; d_table_outs is a HOST array of
+ * nsteps device pointers (entries may be NULL).  With commit the steps are applied on top
+ * of each other and the last table' is installed. */
+int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nsteps,
+                                     int32_t* const* d_table_outs, int commit,
+                                     void* stream);
+/* step + 1 of the last apply that gave up waiting for a peer (~2 s), 0 if none */
+int64_t egpu_peer_last_timeout(egpu_ctx* ctx);
+
 /* Deterministic synthetic request generator on the device (same counter-based
  * RNG as the CPU generators).  dist: 2 = cfg2, 3 = cfg3. */
 int egpu_synth_requests_dev(egpu_ctx* ctx, int dist, uint64_t seed,

@@ -1,0 +1,126 @@
+"""GPU tests of the multi-GPU path that exchanges demand vectors through peer memory
+(CUDA IPC) instead of a collective: world = 1 in-process, and world = 2 as two processes
+that share cuda:0 (IPC works between processes on one device; the round-end multi-GPU
+bench runs the same code across GPUs).  Expected values come from the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world1_shard_step_equals_snapshot(alloc, oracle_c, egpu):
+    import torch
+    w = egpu.synth.workload("cfg4")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    alloc.peer_attach(0, 1, [alloc.peer_export()])
+    s = torch.cuda.current_stream().cuda_stream
+    D, R = 64, 50_003
+    cur_c, cur_m = w["free_core"].copy(), w["free_mem"].copy()
+    for step in range(40):  # more steps than exchange slots
+        rc, rm = egpu.synth.requests(4, 900 + step, R)
+        c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
+        idx = torch.empty(R + 1, dtype=torch.int32, device="cuda")
+        dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+        tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+        alloc.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, s)
+        commit = step % 5 == 4
+        alloc.apply_peers_dev(step, tab.data_ptr(), commit, s)
+        torch.cuda.synchronize()
+        o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(cur_c, cur_m, rc, rm, 4)
+        assert np.array_equal(idx[:R].cpu().numpy(), o_idx)
+        assert np.array_equal(dl.cpu().numpy(), np.concatenate([o_dc, o_dm]))
+        assert np.array_equal(tab.cpu().numpy(), o_tab)
+        if commit:
+            cur_c, cur_m = np.maximum(o_tab[:D], 0), np.maximum(o_tab[D:2 * D], 0)
+    assert alloc.peer_last_timeout == 0
+    g_c, g_m, _ = alloc.table()
+    assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m)
+    alloc.peer_detach()
+
+
+def test_shard_calls_need_attach(alloc, egpu):
+    alloc.set_table([1], [1])
+    with pytest.raises(egpu.EgpuError) as ei:
+        alloc.apply_peers_dev(0)
+    assert ei.value.code == -6
+
+
+def _rank_main(rank, world, conn, peer_conn, steps, R):
+    sys.path.insert(0, ROOT)
+    import torch
+    import elastic_gpu_agent_b200 as e
+    torch.cuda.set_device(0)
+    w = e.synth.workload("cfg3")
+    a = e.BestFitAllocator(0)
+    a.set_table(w["free_core"], w["free_mem"])
+    mine = a.peer_export()
+    peer_conn.send(mine)
+    other = peer_conn.recv()
+    handles = [mine, other] if rank == 0 else [other, mine]
+    a.peer_attach(rank, world, handles)
+    peer_conn.send("attached")
+    assert peer_conn.recv() == "attached"
+    s = torch.cuda.current_stream().cuda_stream
+    D = 8
+    out = []
+    keep = []
+    for step in range(steps):
+        rc, rm = e.synth.requests(3, 70 + step, R, first_row=rank * R)
+        c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
+        idx = torch.empty(R, dtype=torch.int32, device="cuda")
+        dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+        tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+        a.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, s)
+        a.apply_peers_dev(step, tab.data_ptr(), step % 3 == 2, s)
+        keep.append((c, m, idx, dl, tab))
+    torch.cuda.synchronize()
+    for c, m, idx, dl, tab in keep:
+        out.append((idx.cpu().numpy(), dl.cpu().numpy(), tab.cpu().numpy()))
+    fc, fm, ov = a.table()
+    conn.send((rank, out, fc, fm, a.peer_last_timeout))
+    peer_conn.send("done")
+    peer_conn.recv()
+    a.peer_detach()
+    a.close()
+
+
+def test_world2_two_processes_one_gpu(oracle_c, egpu):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    steps, R, world, D = 7, 20_001, 2, 8
+    a_conn, b_conn = ctx.Pipe()          # rank0 <-> rank1
+    res0_r, res0_w = ctx.Pipe(False)
+    res1_r, res1_w = ctx.Pipe(False)
+    p0 = ctx.Process(target=_rank_main, args=(0, world, res0_w, a_conn, steps, R))
+    p1 = ctx.Process(target=_rank_main, args=(1, world, res1_w, b_conn, steps, R))
+    p0.start()
+    p1.start()
+    assert res0_r.poll(180) and res1_r.poll(180), "ranks did not finish"
+    r0, r1 = res0_r.recv(), res1_r.recv()
+    p0.join(60)
+    p1.join(60)
+    assert p0.exitcode == 0 and p1.exitcode == 0
+    assert r0[4] == 0 and r1[4] == 0, "an apply kernel timed out waiting for its peer"
+    w = egpu.synth.workload("cfg3")
+    cur_c, cur_m = w["free_core"].copy(), w["free_mem"].copy()
+    for step in range(steps):
+        tot = np.zeros(2 * D, dtype=np.int64)
+        for rank, res in ((0, r0), (1, r1)):
+            rc, rm = egpu.synth.requests(3, 70 + step, R, first_row=rank * R)
+            o_idx, o_dc, o_dm, _ = oracle_c.snapshot(cur_c, cur_m, rc, rm)
+            idx, dl, tab = res[1][step]
+            assert np.array_equal(idx, o_idx), f"indices rank {rank} step {step}"
+            assert np.array_equal(dl, np.concatenate([o_dc, o_dm]))
+            tot += np.concatenate([o_dc, o_dm])
+        from elastic_gpu_agent_b200 import sharding
+        etab = sharding.combine_demands(cur_c, cur_m, tot[None, :])
+        assert np.array_equal(r0[1][step][2], etab) and np.array_equal(r1[1][step][2], etab)
+        if step % 3 == 2:
+            cur_c, cur_m = np.maximum(etab[:D], 0), np.maximum(etab[D:2 * D], 0)
+    for res in (r0, r1):
+        assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
