@@ -86,6 +86,12 @@ def load() -> C.CDLL:
         "egpu_table_apply_peers_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),
         "egpu_table_apply_peers_multi_dev": (C.c_int, [vp, C.c_uint64, C.c_int, vp, C.c_int, vp]),
         "egpu_peer_last_timeout": (C.c_int64, [vp]),
+        "egpu_device_hash_batch": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp]),
+        "egpu_device_hash": (C.c_int, [vp, vp, C.c_int64, vp]),
+        "egpu_device_locate": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int64)]),
+        "egpu_device_id_format": (C.c_int, [C.c_int32, C.c_int64, C.c_char_p, C.c_int64]),
+        "egpu_device_id_parse": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+        "egpu_preferred_allocation": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int, vp, C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly

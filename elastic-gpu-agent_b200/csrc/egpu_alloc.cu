@@ -852,77 +852,9 @@ replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const
 // =============================================================================
 using namespace egpu;
 
-using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
-                            unsigned long long);
-
-using LutKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
-                           unsigned long long, const egpu::DevLut*);
-
-struct SnapLaunch {
-    SnapKernel fn = nullptr;
-    LutKernel lut_fn = nullptr;  // set instead of fn for the lookup-table scan
-    int threads = 0;
-    size_t smem = 0;
-    int ctas_per_sm = 0;  // 0 = not configured yet on this context
-};
-
-struct egpu_ctx {
-    std::mutex mu;
-    SnapLaunch snap[3][4];            // [sorted, grid, lut][D bucket]
-    DevLut* d_lut = nullptr;
-    XchgBuf* d_xchg = nullptr;        // this rank's exchange buffer (exported to the peers over CUDA IPC)
-    void* peer_open[kMaxRanks] = {};  // peers' buffers as opened here (nullptr for own rank)
-    int world = 1, rank = 0;
-    bool attached = false;
-    bool lut_dirty = true;            // table changed since the lookup tables were built
-    int dev = -1;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    DevState* d_state = nullptr;
-    bool has_table = false;
-    int D = 0;
-    int variant = EGPU_VARIANT_AUTO;
-    int64_t launches = 0;
-    // staging for the host-buffer entry points
-    int32_t* d_req_core = nullptr;
-    int32_t* d_req_mem = nullptr;
-    int32_t* d_idx = nullptr;
-    int64_t d_cap_rows = 0;
-    long long* d_delta = nullptr;     // int64[2*64]
-    int32_t* d_table_out = nullptr;   // int32[3*64]
-    long long* h_delta = nullptr;     // pinned
-    long long* h_delta_dev = nullptr; // its device-visible alias
-    bool no_zero_copy = false;        // EGPU_NO_ZERO_COPY=1: always stage through HBM
-    int32_t* h_table = nullptr;       // pinned int32[3*64]
-    signed char* d_live = nullptr;
-    int64_t d_live_cap = 0;
-    // bookkeeping for programmatic dependent launch (see launch_snapshot)
-    bool prev_is_scan = false;        // the last kernel this context launched was a snapshot scan ...
-    bool prev_changes_table = false;  // ... and it may rewrite the table (commit)
-    cudaStream_t prev_stream = nullptr;
-    uint64_t seq = 0;                 // scans launched (epilogue slot = seq mod kEpiSlots)
-    int group_len = 0;                // launches since (and including) the last fully ordered one
-    struct Range { uintptr_t lo, hi; } group_out[3 * kPipeGroupMax];  // their output ranges
-    int pipe_group = 16;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
-    int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
-    int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
-    int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
-    char last_err[256] = {0};
-};
+#include "egpu_ctx.h"
 
 namespace {
-
-int cuda_fail(egpu_ctx* ctx, cudaError_t e, const char* what) {
-    if (ctx) std::snprintf(ctx->last_err, sizeof ctx->last_err, "%s: %s", what, cudaGetErrorString(e));
-    (void)cudaGetLastError();
-    return e == cudaErrorMemoryAllocation ? EGPU_ERR_NOMEM : EGPU_ERR_CUDA;
-}
-
-#define EGPU_CUDA(ctx, call)                                   \
-    do {                                                       \
-        cudaError_t e__ = (call);                              \
-        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
-    } while (0)
 
 template <int DT, int THREADS>
 SnapLaunch make_launch(bool grid_variant) {

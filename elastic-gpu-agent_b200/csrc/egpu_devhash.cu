@@ -1,0 +1,588 @@
+// egpu_devhash.cu — device-set identity on the GPU: types.NewDevice + hash + Equals of
+// elastic-ai/elastic-gpu-agent (pkg/types/device.go:17-54), batched over many ID lists the
+// way KubeletDeviceLocator.Locate needs them (pkg/kube/locator.go:62-90).
+//
+//   sort.Strings(ids); Hash = hex(sha256(strings.Join(ids, ":")))[0:8]
+//
+// Product path (no CPU fallback, nothing from oracle/).  Byte work, HBM/latency bound:
+//   pack      one thread per ID: <= 16 chars of {'-','0'..'9'} -> 4 bits each in a u64,
+//             first character in the top nibble, so u64 order == byte-wise string order
+//   sort      LSD radix sort, 4-bit digits, on (set, key): only as many passes as the
+//             longest ID has characters, plus ceil(log16(n_sets)) for the set index
+//   render    exclusive scan of (len + 1) gives every ID its place in its set's message;
+//             one thread per ID writes the characters and the ':' separator
+//   sha256    one thread per set walks its message in 64-byte blocks (the chain is serial)
+//   locate    candidate set == request set iff same size and all sorted keys equal
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/egpu_devhash.h"
+#include "egpu_ctx.h"
+
+namespace egpu {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                          // items per thread (blocked arrangement)
+constexpr int kSortTile = kSortThreads * kSortItems;   // items per CTA per pass
+
+struct HashErr {
+    int bad;  // != 0: some ID is empty, longer than 16 bytes or has a foreign character
+};
+
+__device__ __forceinline__ uint32_t char_code(unsigned char c) {
+    if (c == '-') return 1u;
+    if (c >= '0' && c <= '9') return 2u + (c - '0');
+    return 0u;  // invalid
+}
+__device__ __forceinline__ char code_char(uint32_t n) { return n == 1u ? '-' : static_cast<char>('0' + (n - 2u)); }
+
+__global__ void pack_ids_kernel(const char* __restrict__ flat, const long long* __restrict__ id_off, long long n_ids,
+                                unsigned long long* __restrict__ key, uint32_t* __restrict__ len1, HashErr* err) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_ids) return;
+    const long long b = id_off[i], e = id_off[i + 1];
+    const long long l = e - b;
+    unsigned long long k = 0;
+    bool ok = l >= 1 && l <= 16;
+    for (int j = 0; j < 16; ++j) {
+        uint32_t code = 0;
+        if (j < l && ok) {
+            code = char_code(static_cast<unsigned char>(flat[b + j]));
+            ok = ok && code != 0u;
+        }
+        k = (k << 4) | code;
+    }
+    if (!ok) {
+        err->bad = 1;
+        k = 0;
+    }
+    key[i] = k;
+    len1[i] = static_cast<uint32_t>(ok ? l : 0) + 1u;  // + ':' (the last one of a set is dropped later)
+}
+
+// ---- LSD radix sort, 4-bit digit, stable -----------------------------------------
+// digit source: shift < 64 -> key nibble, else set-index nibble (shift - 64)
+__device__ __forceinline__ uint32_t digit_of(unsigned long long k, uint32_t s, int shift) {
+    return shift < 64 ? static_cast<uint32_t>(k >> shift) & 15u : (s >> (shift - 64)) & 15u;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ set, long long n, int shift,
+                  uint32_t* __restrict__ hist /* [16][gridDim.x] */) {
+    __shared__ uint32_t sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = static_cast<long long>(blockIdx.x) * kSortTile;
+    uint32_t local[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) local[b] = 0;
+    for (int j = 0; j < kSortItems; ++j) {
+        const long long i = base + threadIdx.x + static_cast<long long>(j) * kSortThreads;  // coalesced: order is irrelevant here
+        if (i < n) {
+            const uint32_t d = digit_of(key[i], set[i], shift);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) local[b] += (d == static_cast<uint32_t>(b));
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, local[b]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh[b], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) hist[threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of hist in (digit major, block minor) order; one CTA
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ hist, int n) {
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warp_sum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n ? hist[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sum[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            warp_sum[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t wprev = (threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t incl = x + wprev + carry;
+        if (i < n) hist[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const unsigned long long* __restrict__ key_in, const uint32_t* __restrict__ set_in, long long n, int shift,
+                     const uint32_t* __restrict__ offs /* scanned hist */, unsigned long long* __restrict__ key_out,
+                     uint32_t* __restrict__ set_out) {
+    // blocked arrangement: thread t owns items [t*kSortItems, (t+1)*kSortItems) of the tile, so a
+    // per-thread count followed by a scan over threads gives STABLE ranks
+    __shared__ uint32_t cnt[16][kSortThreads + 1];
+    const int t = threadIdx.x;
+    const long long base = static_cast<long long>(blockIdx.x) * kSortTile + static_cast<long long>(t) * kSortItems;
+    unsigned long long k[kSortItems];
+    uint32_t s[kSortItems], d[kSortItems];
+    uint32_t local[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) local[b] = 0;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const long long i = base + j;
+        d[j] = 16u;
+        if (i < n) {
+            k[j] = key_in[i];
+            s[j] = set_in[i];
+            d[j] = digit_of(k[j], s[j], shift);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) local[b] += (d[j] == static_cast<uint32_t>(b));
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) cnt[b][t] = local[b];
+    __syncthreads();
+    // exclusive scan of each digit row over the threads: warp w scans rows w, w+8
+    {
+        const int warp = t >> 5, lane = t & 31;
+        for (int row = warp; row < 16; row += kSortThreads / 32) {
+            uint32_t run = 0;
+            for (int c0 = 0; c0 < kSortThreads; c0 += 32) {
+                const uint32_t v = cnt[row][c0 + lane];
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                cnt[row][c0 + lane] = run + x - v;
+                run += __shfl_sync(0xffffffffu, x, 31);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t pos[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) pos[b] = offs[b * gridDim.x + blockIdx.x] + cnt[b][t];
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        if (d[j] < 16u) {
+            uint32_t dst = 0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (d[j] == static_cast<uint32_t>(b)) dst = pos[b]++;
+            key_out[dst] = k[j];
+            set_out[dst] = s[j];
+        }
+    }
+}
+
+// ---- generic exclusive scan of uint32 -> uint64 (message byte offsets) ---------------
+__global__ void __launch_bounds__(1024)
+scan_block_sums_kernel(const uint32_t* __restrict__ v, long long n, unsigned long long* __restrict__ block_sum) {
+    __shared__ unsigned long long sh[32];
+    const long long i = static_cast<long long>(blockIdx.x) * 1024 + threadIdx.x;
+    unsigned long long x = i < n ? v[i] : 0ull;
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        x = sh[threadIdx.x];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (threadIdx.x == 0) block_sum[blockIdx.x] = x;
+    }
+}
+__global__ void scan_serial_kernel(unsigned long long* __restrict__ a, long long n) {  // n = #blocks, small
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (long long i = 0; i < n; ++i) {
+            const unsigned long long v = a[i];
+            a[i] = run;
+            run += v;
+        }
+    }
+}
+__global__ void __launch_bounds__(1024)
+scan_apply_kernel(const uint32_t* __restrict__ v, long long n, const unsigned long long* __restrict__ block_off,
+                  unsigned long long* __restrict__ out /* [n + 1] */) {
+    __shared__ unsigned long long warp_sum[32];
+    const long long i = static_cast<long long>(blockIdx.x) * 1024 + threadIdx.x;
+    const unsigned long long val = i < n ? v[i] : 0ull;
+    unsigned long long x = val;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long w = warp_sum[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+            if (threadIdx.x >= o) w += y;
+        }
+        warp_sum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const unsigned long long wprev = (threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0ull;
+    const unsigned long long incl = x + wprev + block_off[blockIdx.x];
+    if (i < n) {
+        out[i] = incl - val;
+        if (i == n - 1) out[n] = incl;
+    }
+}
+
+// after the sort: length (+1) of every sorted ID, recovered from its key
+__global__ void sorted_len_kernel(const unsigned long long* __restrict__ key, long long n, uint32_t* __restrict__ len1) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    // characters are left-aligned: length = 16 - (trailing zero nibbles)
+    const int tz = k ? (__ffsll(static_cast<long long>(k)) - 1) >> 2 : 16;
+    len1[i] = static_cast<uint32_t>(16 - tz) + 1u;
+}
+
+// message layout: set s starts at msg_base[s] (64-byte aligned); ID i of the sorted array
+// sits at msg_base[s] + (pref[i] - pref[set_start[s]])
+__global__ void set_layout_kernel(const long long* __restrict__ set_off, long long n_sets,
+                                  const unsigned long long* __restrict__ pref, unsigned long long* __restrict__ msg_base,
+                                  unsigned long long* __restrict__ msg_len) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (long long s = 0; s < n_sets; ++s) {
+            const unsigned long long bytes = pref[set_off[s + 1]] - pref[set_off[s]];
+            const unsigned long long len = bytes ? bytes - 1 : 0;  // no ':' after the last ID
+            msg_base[s] = run;
+            msg_len[s] = len;
+            run += (len + 64 + 63) & ~63ull;  // room for SHA-256 padding, keep 64-byte alignment
+        }
+        msg_base[n_sets] = run;
+    }
+}
+
+__global__ void render_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ set, long long n,
+                              const long long* __restrict__ set_off, const unsigned long long* __restrict__ pref,
+                              const unsigned long long* __restrict__ msg_base, unsigned char* __restrict__ msg) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = set[i];
+    unsigned char* p = msg + msg_base[s] + (pref[i] - pref[set_off[s]]);
+    const unsigned long long k = key[i];
+    int l = 0;
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t c = static_cast<uint32_t>(k >> (60 - 4 * j)) & 15u;
+        if (!c) break;
+        p[l++] = static_cast<unsigned char>(code_char(c));
+    }
+    if (i + 1 < set_off[s + 1]) p[l] = ':';
+}
+
+// ---- SHA-256 (FIPS 180-4), one message per thread -------------------------------------
+__constant__ uint32_t kSha[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+__global__ void sha256_sets_kernel(unsigned char* __restrict__ msg, const unsigned long long* __restrict__ msg_base,
+                                   const unsigned long long* __restrict__ msg_len, long long n_sets,
+                                   uint32_t* __restrict__ digest /* [n_sets][8] */) {
+    const long long s = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s >= n_sets) return;
+    unsigned char* m = msg + msg_base[s];
+    const unsigned long long len = msg_len[s];
+    // padding in place (the layout reserved the room): 0x80, zeros, 64-bit big-endian bit length
+    const unsigned long long total = ((len + 8) / 64 + 1) * 64;
+    m[len] = 0x80;
+    for (unsigned long long i = len + 1; i < total - 8; ++i) m[i] = 0;
+    const unsigned long long bits = len * 8;
+    for (int i = 0; i < 8; ++i) m[total - 1 - i] = static_cast<unsigned char>(bits >> (8 * i));
+    uint32_t h0 = 0x6a09e667, h1 = 0xbb67ae85, h2 = 0x3c6ef372, h3 = 0xa54ff53a, h4 = 0x510e527f, h5 = 0x9b05688c,
+             h6 = 0x1f83d9ab, h7 = 0x5be0cd19;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(m);  // 64-byte aligned base
+    for (unsigned long long blk = 0; blk < total / 64; ++blk) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = __byte_perm(words[blk * 16 + i], 0, 0x0123);  // big-endian load
+        uint32_t a = h0, b = h1, c = h2, d = h3, e = h4, f = h5, g = h6, h = h7;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            uint32_t wi;
+            if (i < 16) {
+                wi = w[i];
+            } else {
+                const uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+                const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+                w[i & 15] = wi;
+            }
+            const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t t1 = h + S1 + ch + kSha[i] + wi;
+            const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t t2 = S0 + mj;
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; h5 += f; h6 += g; h7 += h;
+    }
+    uint32_t* o = digest + s * 8;
+    o[0] = h0; o[1] = h1; o[2] = h2; o[3] = h3; o[4] = h4; o[5] = h5; o[6] = h6; o[7] = h7;
+}
+
+// Device.Equals against set 0: one thread per candidate ID compares with the request's ID
+// at the same sorted rank; any difference clears the candidate's flag
+__global__ void locate_compare_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ set,
+                                      long long n, const long long* __restrict__ set_off, int* __restrict__ equal) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = set[i];
+    if (s == 0) return;
+    const long long n0 = set_off[1] - set_off[0];
+    const long long ns = set_off[s + 1] - set_off[s];
+    if (ns != n0) {
+        equal[s] = 0;
+        return;
+    }
+    if (key[i] != key[set_off[0] + (i - set_off[s])]) equal[s] = 0;
+}
+__global__ void locate_init_kernel(int* __restrict__ equal, const long long* __restrict__ set_off, long long n_sets) {
+    const long long s = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s >= n_sets) return;
+    // sets of a different size never match; equal-size sets start as "equal" and are knocked out
+    equal[s] = (s > 0 && (set_off[s + 1] - set_off[s]) == (set_off[1] - set_off[0])) ? 1 : 0;
+}
+
+}  // namespace egpu
+
+using namespace egpu;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T>
+    T* as() { return static_cast<T*>(p); }
+};
+
+// common pipeline: pack, sort, layout, render, hash.  Leaves digests on the device and, for
+// locate, the sorted keys.  All on the context's stream.
+struct HashRun {
+    DevBuf flat, id_off, set_off, set_of, key_a, key_b, set_a, set_b, len1, pref, blk, hist, msg_base, msg_len, msg, digest, err,
+        equal;
+    unsigned long long* sorted_key = nullptr;
+    uint32_t* sorted_set = nullptr;
+};
+
+int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_offsets, int64_t n_ids,
+             const int64_t* set_offsets, int64_t n_sets, bool need_digest) {
+    cudaStream_t s = ctx->stream;
+    if (n_ids < 0 || n_sets < 1 || !id_offsets || !set_offsets) return EGPU_ERR_INVALID;
+    if (set_offsets[0] != 0 || set_offsets[n_sets] != n_ids || id_offsets[0] != 0) return EGPU_ERR_INVALID;
+    if (n_sets > (1ll << 24) || n_ids > (1ll << 31) - 1) return EGPU_ERR_INVALID;
+    const int64_t flat_bytes = id_offsets[n_ids];
+    if (flat_bytes < 0 || (flat_bytes > 0 && !ids_flat)) return EGPU_ERR_INVALID;
+    std::vector<uint32_t> set_of(static_cast<size_t>(n_ids));
+    int64_t max_len = 0;
+    for (int64_t q = 0; q < n_sets; ++q) {
+        if (set_offsets[q + 1] < set_offsets[q]) return EGPU_ERR_INVALID;
+        for (int64_t i = set_offsets[q]; i < set_offsets[q + 1]; ++i) set_of[i] = static_cast<uint32_t>(q);
+    }
+    for (int64_t i = 0; i < n_ids; ++i) {
+        const int64_t l = id_offsets[i + 1] - id_offsets[i];
+        if (l < 1 || l > 16) return EGPU_ERR_PARSE;
+        max_len = l > max_len ? l : max_len;
+    }
+    const size_t n = static_cast<size_t>(n_ids);
+    const int64_t tiles = (n_ids + kSortTile - 1) / kSortTile;
+    EGPU_CUDA(ctx, r.flat.alloc(static_cast<size_t>(flat_bytes)));
+    EGPU_CUDA(ctx, r.id_off.alloc(sizeof(long long) * (n + 1)));
+    EGPU_CUDA(ctx, r.set_off.alloc(sizeof(long long) * (n_sets + 1)));
+    EGPU_CUDA(ctx, r.key_a.alloc(8 * n));
+    EGPU_CUDA(ctx, r.key_b.alloc(8 * n));
+    EGPU_CUDA(ctx, r.set_a.alloc(4 * n));
+    EGPU_CUDA(ctx, r.set_b.alloc(4 * n));
+    EGPU_CUDA(ctx, r.len1.alloc(4 * n));
+    EGPU_CUDA(ctx, r.pref.alloc(8 * (n + 1)));
+    EGPU_CUDA(ctx, r.blk.alloc(8 * ((n + 1023) / 1024 + 1)));
+    EGPU_CUDA(ctx, r.hist.alloc(4 * 16 * static_cast<size_t>(tiles > 0 ? tiles : 1)));
+    EGPU_CUDA(ctx, r.msg_base.alloc(8 * (n_sets + 1)));
+    EGPU_CUDA(ctx, r.msg_len.alloc(8 * n_sets));
+    EGPU_CUDA(ctx, r.digest.alloc(32 * n_sets));
+    EGPU_CUDA(ctx, r.err.alloc(sizeof(HashErr)));
+    EGPU_CUDA(ctx, cudaMemsetAsync(r.err.p, 0, sizeof(HashErr), s));
+    if (flat_bytes) EGPU_CUDA(ctx, cudaMemcpyAsync(r.flat.p, ids_flat, flat_bytes, cudaMemcpyHostToDevice, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(r.id_off.p, id_offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(r.set_off.p, set_offsets, sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice, s));
+    if (n) EGPU_CUDA(ctx, cudaMemcpyAsync(r.set_a.p, set_of.data(), 4 * n, cudaMemcpyHostToDevice, s));
+    unsigned long long* ka = r.key_a.as<unsigned long long>();
+    unsigned long long* kb = r.key_b.as<unsigned long long>();
+    uint32_t* sa = r.set_a.as<uint32_t>();
+    uint32_t* sb = r.set_b.as<uint32_t>();
+    const unsigned nb256 = static_cast<unsigned>((n_ids + 255) / 256);
+    if (n) {
+        pack_ids_kernel<<<nb256, 256, 0, s>>>(r.flat.as<char>(), r.id_off.as<long long>(), n_ids, ka, r.len1.as<uint32_t>(),
+                                              r.err.as<HashErr>());
+        ctx->launches += 1;
+        // LSD: last character first, then the set index
+        int set_digits = 0;
+        while ((1ll << (4 * set_digits)) < n_sets) ++set_digits;
+        std::vector<int> shifts;
+        for (int j = static_cast<int>(max_len) - 1; j >= 0; --j) shifts.push_back(60 - 4 * j);
+        for (int j = 0; j < set_digits; ++j) shifts.push_back(64 + 4 * j);
+        for (int shift : shifts) {
+            radix_hist_kernel<<<static_cast<unsigned>(tiles), kSortThreads, 0, s>>>(ka, sa, n_ids, shift, r.hist.as<uint32_t>());
+            radix_scan_kernel<<<1, 1024, 0, s>>>(r.hist.as<uint32_t>(), static_cast<int>(16 * tiles));
+            radix_scatter_kernel<<<static_cast<unsigned>(tiles), kSortThreads, 0, s>>>(ka, sa, n_ids, shift, r.hist.as<uint32_t>(), kb, sb);
+            ctx->launches += 3;
+            std::swap(ka, kb);
+            std::swap(sa, sb);
+        }
+        EGPU_CUDA(ctx, cudaGetLastError());
+    }
+    r.sorted_key = ka;
+    r.sorted_set = sa;
+    HashErr herr{0};
+    if (need_digest) {
+        const unsigned nblk = static_cast<unsigned>((n_ids + 1023) / 1024);
+        if (n) {
+            sorted_len_kernel<<<nb256, 256, 0, s>>>(ka, n_ids, r.len1.as<uint32_t>());
+            scan_block_sums_kernel<<<nblk, 1024, 0, s>>>(r.len1.as<uint32_t>(), n_ids, r.blk.as<unsigned long long>());
+            scan_serial_kernel<<<1, 32, 0, s>>>(r.blk.as<unsigned long long>(), nblk);
+            scan_apply_kernel<<<nblk, 1024, 0, s>>>(r.len1.as<uint32_t>(), n_ids, r.blk.as<unsigned long long>(),
+                                                    r.pref.as<unsigned long long>());
+            ctx->launches += 4;
+        } else {
+            EGPU_CUDA(ctx, cudaMemsetAsync(r.pref.p, 0, 8, s));
+        }
+        set_layout_kernel<<<1, 32, 0, s>>>(r.set_off.as<long long>(), n_sets, r.pref.as<unsigned long long>(),
+                                           r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>());
+        ctx->launches += 1;
+        // message buffer size: every ID contributes len + 1 <= 17 bytes, every set <= 127 bytes of padding
+        const size_t msg_cap = static_cast<size_t>(flat_bytes) + n + static_cast<size_t>(n_sets) * 128 + 64;
+        EGPU_CUDA(ctx, r.msg.alloc(msg_cap));
+        if (n) {
+            render_kernel<<<nb256, 256, 0, s>>>(ka, sa, n_ids, r.set_off.as<long long>(), r.pref.as<unsigned long long>(),
+                                                r.msg_base.as<unsigned long long>(), r.msg.as<unsigned char>());
+            ctx->launches += 1;
+        }
+        sha256_sets_kernel<<<static_cast<unsigned>((n_sets + 63) / 64), 64, 0, s>>>(
+            r.msg.as<unsigned char>(), r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>(), n_sets,
+            r.digest.as<uint32_t>());
+        ctx->launches += 1;
+        EGPU_CUDA(ctx, cudaGetLastError());
+    }
+    EGPU_CUDA(ctx, cudaMemcpyAsync(&herr, r.err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->prev_is_scan = false;
+    if (herr.bad) return EGPU_ERR_PARSE;
+    return EGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int egpu_device_hash_batch(egpu_ctx* ctx, const char* ids_flat, const int64_t* id_offsets, int64_t n_ids,
+                           const int64_t* set_offsets, int64_t n_sets, char* out_hash8, uint8_t* out_digest) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    HashRun r;
+    const int rc = run_hash(ctx, r, ids_flat, id_offsets, n_ids, set_offsets, n_sets, true);
+    if (rc != EGPU_OK) return rc;
+    std::vector<uint32_t> dg(static_cast<size_t>(n_sets) * 8);
+    EGPU_CUDA(ctx, cudaMemcpy(dg.data(), r.digest.p, 32 * n_sets, cudaMemcpyDeviceToHost));
+    static const char hex[] = "0123456789abcdef";
+    for (int64_t q = 0; q < n_sets; ++q) {
+        if (out_digest)
+            for (int w = 0; w < 8; ++w)
+                for (int b = 0; b < 4; ++b) out_digest[q * 32 + w * 4 + b] = static_cast<uint8_t>(dg[q * 8 + w] >> (24 - 8 * b));
+        if (out_hash8) {
+            const uint32_t w0 = dg[q * 8];
+            for (int k = 0; k < 8; ++k) out_hash8[q * 9 + k] = hex[(w0 >> (28 - 4 * k)) & 15u];
+            out_hash8[q * 9 + 8] = 0;
+        }
+    }
+    return EGPU_OK;
+}
+
+int egpu_device_hash(egpu_ctx* ctx, const char* const* ids, int64_t n, char* out_hash8) {
+    if (!ctx || n < 0 || (n > 0 && !ids) || !out_hash8) return EGPU_ERR_INVALID;
+    std::vector<char> flat;
+    std::vector<int64_t> off(static_cast<size_t>(n) + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (!ids[i]) return EGPU_ERR_INVALID;
+        const size_t l = std::strlen(ids[i]);
+        flat.insert(flat.end(), ids[i], ids[i] + l);
+        off[i + 1] = static_cast<int64_t>(flat.size());
+    }
+    const int64_t sets[2] = {0, n};
+    return egpu_device_hash_batch(ctx, flat.data(), off.data(), n, sets, 1, out_hash8, nullptr);
+}
+
+int egpu_device_locate(egpu_ctx* ctx, const char* ids_flat, const int64_t* id_offsets, int64_t n_ids,
+                       const int64_t* set_offsets, int64_t n_sets, int64_t* out_match) {
+    if (!ctx || !out_match) return EGPU_ERR_INVALID;
+    *out_match = -1;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    HashRun r;
+    // Equals = same hash AND same sorted list; comparing the sorted lists decides both, so the
+    // digests are not needed here
+    const int rc = run_hash(ctx, r, ids_flat, id_offsets, n_ids, set_offsets, n_sets, false);
+    if (rc != EGPU_OK) return rc;
+    if (n_sets < 2) return EGPU_OK;
+    cudaStream_t s = ctx->stream;
+    EGPU_CUDA(ctx, r.equal.alloc(sizeof(int) * n_sets));
+    locate_init_kernel<<<static_cast<unsigned>((n_sets + 255) / 256), 256, 0, s>>>(r.equal.as<int>(), r.set_off.as<long long>(), n_sets);
+    if (n_ids)
+        locate_compare_kernel<<<static_cast<unsigned>((n_ids + 255) / 256), 256, 0, s>>>(r.sorted_key, r.sorted_set, n_ids,
+                                                                                         r.set_off.as<long long>(), r.equal.as<int>());
+    ctx->launches += 2;
+    EGPU_CUDA(ctx, cudaGetLastError());
+    std::vector<int> eq(static_cast<size_t>(n_sets));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(eq.data(), r.equal.p, sizeof(int) * n_sets, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int64_t q = 1; q < n_sets; ++q)
+        if (eq[q]) {
+            *out_match = q;
+            break;
+        }
+    return EGPU_OK;
+}
+
+}  // extern "C"

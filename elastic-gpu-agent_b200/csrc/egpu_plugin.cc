@@ -1,0 +1,141 @@
+// egpu_plugin.cc — host logic between the kubelet device-plugin messages and the CUDA
+// best-fit scan: ID codec ("%d-%02d", pkg/plugins/gpushare.go:28,163) and
+// GetPreferredAllocation for one container (the stub at pkg/plugins/base.go:94-96).
+// Plain C++; the device choice is delegated to egpu_bestfit_batch (CUDA).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/egpu_plugin.h"
+
+extern "C" {
+
+int egpu_device_id_format(int32_t gpu, int64_t unit, char* out, int64_t cap) {
+    if (!out || cap <= 0 || gpu < 0 || unit < 0) return EGPU_ERR_INVALID;
+    const int n = std::snprintf(out, static_cast<size_t>(cap), "%d-%02lld", gpu, static_cast<long long>(unit));
+    if (n < 0 || n >= cap) return EGPU_ERR_INVALID;
+    return n;
+}
+
+int egpu_device_id_parse(const char* id, int32_t* gpu, int64_t* unit) {
+    if (!id || !gpu || !unit) return EGPU_ERR_INVALID;
+    const char* p = id;
+    if (*p < '0' || *p > '9') return EGPU_ERR_PARSE;
+    int64_t g = 0;
+    int digits = 0;
+    while (*p >= '0' && *p <= '9') {
+        g = g * 10 + (*p - '0');
+        if (++digits > 9) return EGPU_ERR_PARSE;
+        ++p;
+    }
+    if (digits > 1 && id[0] == '0') return EGPU_ERR_PARSE;  // %d never pads the GPU index
+    if (*p != '-') return EGPU_ERR_PARSE;
+    ++p;
+    const char* u0 = p;
+    int64_t u = 0;
+    digits = 0;
+    while (*p >= '0' && *p <= '9') {
+        u = u * 10 + (*p - '0');
+        if (++digits > 15) return EGPU_ERR_PARSE;
+        ++p;
+    }
+    if (*p != '\0' || digits < 2) return EGPU_ERR_PARSE;       // %02d: at least two digits
+    if (digits > 2 && u0[0] == '0') return EGPU_ERR_PARSE;     // padding only up to two digits
+    *gpu = static_cast<int32_t>(g);
+    *unit = u;
+    return EGPU_OK;
+}
+
+int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, int64_t n_available,
+                              const char* const* must_include_ids, int64_t n_must, int32_t allocation_size,
+                              int resource, int32_t* out_positions, int32_t* out_gpu) {
+    if (!ctx || n_available < 0 || n_must < 0 || allocation_size < 0) return EGPU_ERR_INVALID;
+    if ((n_available > 0 && !available_ids) || (n_must > 0 && !must_include_ids)) return EGPU_ERR_INVALID;
+    if (allocation_size > 0 && !out_positions) return EGPU_ERR_INVALID;
+    if (resource != EGPU_RESOURCE_CORE && resource != EGPU_RESOURCE_MEM) return EGPU_ERR_INVALID;
+    if (n_available > 0x7fffffffll) return EGPU_ERR_INVALID;
+    if (n_must > allocation_size) return EGPU_ERR_UNSAT;
+
+    // 1. IDs -> (gpu, unit); per-GPU availability = the free table of this request
+    std::vector<int32_t> gpu_of(static_cast<size_t>(n_available));
+    std::vector<int64_t> unit_of(static_cast<size_t>(n_available));
+    int32_t D = 0;
+    for (int64_t i = 0; i < n_available; ++i) {
+        const int rc = egpu_device_id_parse(available_ids[i], &gpu_of[i], &unit_of[i]);
+        if (rc != EGPU_OK) return rc;
+        if (gpu_of[i] >= EGPU_MAX_DEVICES) return EGPU_ERR_INVALID;
+        D = std::max(D, gpu_of[i] + 1);
+    }
+    if (D == 0) return allocation_size == 0 ? EGPU_OK : EGPU_ERR_UNSAT;
+    std::vector<int64_t> count(static_cast<size_t>(D), 0);
+    for (int64_t i = 0; i < n_available; ++i) count[gpu_of[i]] += 1;
+
+    // 2. must-include IDs pin the GPU
+    int32_t pinned = -1;
+    std::unordered_map<std::string, int32_t> pos_of;
+    if (n_must > 0) {
+        pos_of.reserve(static_cast<size_t>(n_available) * 2);
+        for (int64_t i = 0; i < n_available; ++i) pos_of.emplace(available_ids[i], static_cast<int32_t>(i));
+        for (int64_t k = 0; k < n_must; ++k) {
+            int32_t g;
+            int64_t u;
+            const int rc = egpu_device_id_parse(must_include_ids[k], &g, &u);
+            if (rc != EGPU_OK) return rc;
+            if (pos_of.find(must_include_ids[k]) == pos_of.end()) return EGPU_ERR_UNSAT;  // kubelet promises must ⊆ available
+            if (pinned >= 0 && g != pinned) return EGPU_ERR_UNSAT;                        // v1: one GPU per container
+            pinned = g;
+        }
+    }
+
+    // 3. the choice: CUDA best-fit over the availability table
+    const int64_t cap_units = resource == EGPU_RESOURCE_CORE ? EGPU_CORE_MAX : EGPU_MEM_MAX;
+    std::vector<int32_t> free_core(static_cast<size_t>(D)), free_mem(static_cast<size_t>(D));
+    for (int32_t d = 0; d < D; ++d) {
+        const int32_t c = static_cast<int32_t>(std::min<int64_t>(count[d], cap_units));
+        const bool usable = pinned < 0 || d == pinned;
+        free_core[d] = resource == EGPU_RESOURCE_CORE ? (usable ? c : 0) : (usable ? EGPU_CORE_MAX : 0);
+        free_mem[d] = resource == EGPU_RESOURCE_MEM ? (usable ? c : 0) : (usable ? EGPU_MEM_MAX : 0);
+    }
+    // table_set + scan must not interleave with another preferred-allocation call on this
+    // context (each call installs its own table; use a context dedicated to these queries)
+    static std::mutex pair_mu;
+    std::lock_guard<std::mutex> pair_lock(pair_mu);
+    int rc = egpu_table_set(ctx, free_core.data(), free_mem.data(), D);
+    if (rc != EGPU_OK) return rc;
+    // a request for 0 units of the constrained resource still needs 1 unit of the other
+    // dimension on unusable GPUs to be excluded: unusable rows are (0, 0), request >= (0, 0)
+    // would fit them, so ask for one unit of the unconstrained dimension
+    int32_t req_core = resource == EGPU_RESOURCE_CORE ? allocation_size : 1;
+    int32_t req_mem = resource == EGPU_RESOURCE_MEM ? allocation_size : 1;
+    if (resource == EGPU_RESOURCE_CORE && allocation_size > EGPU_CORE_MAX) return EGPU_ERR_UNSAT;  // >100 core = several GPUs: not v1
+    int32_t idx = -1;
+    rc = egpu_bestfit_batch(ctx, &req_core, &req_mem, 1, &idx, nullptr, nullptr, 0);
+    if (rc != EGPU_OK) return rc;
+    if (idx < 0) return EGPU_ERR_UNSAT;
+    if (out_gpu) *out_gpu = idx;
+
+    // 4. IDs of the chosen GPU: must-include first, then ascending unit number
+    std::vector<char> taken(static_cast<size_t>(n_available), 0);
+    int32_t n_out = 0;
+    for (int64_t k = 0; k < n_must; ++k) {
+        const int32_t p = pos_of[must_include_ids[k]];
+        if (!taken[p]) {
+            taken[p] = 1;
+            out_positions[n_out++] = p;
+        }
+    }
+    std::vector<int32_t> cand;
+    for (int64_t i = 0; i < n_available; ++i)
+        if (gpu_of[i] == idx && !taken[i]) cand.push_back(static_cast<int32_t>(i));
+    std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) {
+        return unit_of[a] != unit_of[b] ? unit_of[a] < unit_of[b] : a < b;
+    });
+    for (size_t k = 0; k < cand.size() && n_out < allocation_size; ++k) out_positions[n_out++] = cand[k];
+    return n_out == allocation_size ? EGPU_OK : EGPU_ERR_UNSAT;
+}
+
+}  // extern "C"

@@ -35,6 +35,10 @@ def load() -> C.CDLL:
         lib.oracle_bestfit_snapshot.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int]
         lib.oracle_replay.restype = C.c_int
         lib.oracle_replay.argtypes = [vp, vp, C.c_int32, vp, vp, vp, C.c_int64, vp]
+        lib.oracle_device_hash.restype = C.c_int
+        lib.oracle_device_hash.argtypes = [vp, C.c_int64, vp, vp]
+        lib.oracle_sha256.restype = None
+        lib.oracle_sha256.argtypes = [vp, C.c_uint64, vp]
         lib.oracle_max_threads.restype = C.c_int
         lib.oracle_max_threads.argtypes = []
         _lib = lib
@@ -114,3 +118,19 @@ def replay(free_core, free_mem, kind, a, b):
     if r != 0:
         raise ValueError(f"oracle_replay failed: {r}")
     return out, fc, fm
+
+
+def device_hash(ids) -> str:
+    """types.NewDevice(...).Hash per pkg/types/device.go:17-25,49-54 (C restatement)."""
+    arr = (C.c_char_p * max(1, len(ids)))(*[s.encode() for s in ids])
+    out = C.create_string_buffer(9)
+    r = load().oracle_device_hash(arr, len(ids), out, None)
+    if r != 0:
+        raise ValueError(f"oracle_device_hash failed: {r}")
+    return out.value.decode()
+
+
+def sha256(data: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    load().oracle_sha256(C.c_char_p(data), len(data), out)
+    return out.raw
