@@ -466,6 +466,61 @@ def main():
             del rs, g
             torch.cuda.empty_cache()
 
+    # ---- the rows either side of the scan (N = 1 only): sequential replay, device-set identity
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_sweep:
+        from oracle import oracle_c
+        # cfg5: 100k interleaved ALLOC/FREE events through egpu_replay (host buffers, one warp)
+        w5 = e.synth.workload("cfg5")
+        kind, ea, eb = e.synth.churn_events(w5["seed"], w5["R"])
+        alloc.set_table(w5["free_core"], w5["free_mem"])
+        got = alloc.replay(kind, ea, eb)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            alloc.set_table(w5["free_core"], w5["free_mem"])
+            got = alloc.replay(kind, ea, eb)
+        dt_g = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            exp, efc, efm = oracle_c.replay(w5["free_core"], w5["free_mem"], kind, ea, eb)
+        dt_c = (time.perf_counter() - t0) / reps
+        gfc, gfm, _ = alloc.table()
+        extra["cfg5_churn_replay"] = {
+            "events": int(w5["R"]), "gpu_events_per_s_e2e": w5["R"] / dt_g, "gpu_ms_e2e": 1e3 * dt_g,
+            "cpu_port_events_per_s": w5["R"] / dt_c, "cpu_ms": 1e3 * dt_c, "cpu_threads": 1,
+            "bit_exact": bool(np.array_equal(got, exp) and np.array_equal(gfc, efc) and np.array_equal(gfm, efm)),
+            "note": "serial dependence chain: one GPU warp vs one CPU core; the CPU is expected to win (DESIGN.md 4.3)"}
+        # Locate at node scale: 1 request + 96 candidate containers x 4096..16384 memory IDs
+        import hashlib
+        import random
+        from elastic_gpu_agent_b200 import devhash
+        rng = random.Random(11)
+        sets = [["%d-%02d" % (c % 8, j) for j in rng.sample(range(183359), rng.choice([4096, 8192, 16384]))] for c in range(96)]
+        req = list(sets[77])
+        rng.shuffle(req)
+        flat, id_off, set_off = devhash.flatten(sets)             # marshalling is not timed on either side
+        flat_l, id_off_l, set_off_l = devhash.flatten([req] + sets)
+        devhash.device_hashes(alloc, sets[:2])  # warm-up
+        t0 = time.perf_counter()
+        hs = devhash.device_hashes_flat(alloc, flat, id_off, set_off)
+        dt_h = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        m = devhash.locate_flat(alloc, flat_l, id_off_l, set_off_l)
+        dt_l = time.perf_counter() - t0
+        calls = [oracle_c.device_hash_prepared(x) for x in sets]
+        t0 = time.perf_counter()
+        ref = [c[0]() for c in calls]
+        dt_o = time.perf_counter() - t0
+        n_ids = sum(len(x) for x in sets)
+        extra["device_set_identity"] = {
+            "sets": len(sets), "ids": n_ids, "gpu_hash_batch_ms_e2e": 1e3 * dt_h, "gpu_locate_ms_e2e": 1e3 * dt_l,
+            "cpu_port_ms": 1e3 * dt_o, "cpu_threads": 1, "locate_found": m,
+            "bit_exact_vs_reference_formula": bool(hs == ref and all(
+                h == hashlib.sha256(":".join(sorted(x)).encode()).hexdigest()[:8] for h, x in zip(hs[:8], sets[:8])) and m == 77),
+            "note": "types.NewDevice + hash over every candidate container, as KubeletDeviceLocator.Locate does per container start; "
+                    "C-ABI calls only (host buffers in, hashes out: H2D, sort, render, SHA-256, D2H); CPU port = qsort + SHA-256 in C, one thread"}
+
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -509,6 +564,7 @@ def main():
             "clocks": clocks,
             "parity_vs_oracle": parity,
             "sweep": sweep,
+            "next_rows": extra,
         }
         print(json.dumps(line), flush=True)
 

@@ -1118,6 +1118,7 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
     for (int r = 0; r < kMaxRanks; ++r)
         if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
     cudaFree(ctx->d_xchg);
+    cudaFree(ctx->arena);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_req_core);

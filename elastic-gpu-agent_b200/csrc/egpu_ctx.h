@@ -67,6 +67,9 @@ struct egpu_ctx {
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
+    // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
+    void* arena = nullptr;
+    size_t arena_cap = 0;
     char last_err[256] = {0};
 };
 

@@ -388,12 +388,31 @@ using namespace egpu;
 
 namespace {
 
+// Buffers are carved from the context's grow-only arena: cudaMalloc/cudaFree per call
+// would cost more than the kernels.  plan() sizes it, alloc() hands out 256-byte aligned
+// pieces; the arena is only touched under the context mutex.
+struct Arena {
+    egpu_ctx* ctx;
+    size_t used = 0;
+    explicit Arena(egpu_ctx* c) : ctx(c) {}
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= ctx->arena_cap) return cudaSuccess;
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+        size_t cap = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&ctx->arena, cap);
+        if (e == cudaSuccess) ctx->arena_cap = cap;
+        return e;
+    }
+    void* take(size_t bytes) {
+        void* p = static_cast<char*>(ctx->arena) + used;
+        used += (bytes + 255) & ~static_cast<size_t>(255);
+        return p;
+    }
+};
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
     template <class T>
     T* as() { return static_cast<T*>(p); }
 };
@@ -428,21 +447,19 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
     }
     const size_t n = static_cast<size_t>(n_ids);
     const int64_t tiles = (n_ids + kSortTile - 1) / kSortTile;
-    EGPU_CUDA(ctx, r.flat.alloc(static_cast<size_t>(flat_bytes)));
-    EGPU_CUDA(ctx, r.id_off.alloc(sizeof(long long) * (n + 1)));
-    EGPU_CUDA(ctx, r.set_off.alloc(sizeof(long long) * (n_sets + 1)));
-    EGPU_CUDA(ctx, r.key_a.alloc(8 * n));
-    EGPU_CUDA(ctx, r.key_b.alloc(8 * n));
-    EGPU_CUDA(ctx, r.set_a.alloc(4 * n));
-    EGPU_CUDA(ctx, r.set_b.alloc(4 * n));
-    EGPU_CUDA(ctx, r.len1.alloc(4 * n));
-    EGPU_CUDA(ctx, r.pref.alloc(8 * (n + 1)));
-    EGPU_CUDA(ctx, r.blk.alloc(8 * ((n + 1023) / 1024 + 1)));
-    EGPU_CUDA(ctx, r.hist.alloc(4 * 16 * static_cast<size_t>(tiles > 0 ? tiles : 1)));
-    EGPU_CUDA(ctx, r.msg_base.alloc(8 * (n_sets + 1)));
-    EGPU_CUDA(ctx, r.msg_len.alloc(8 * n_sets));
-    EGPU_CUDA(ctx, r.digest.alloc(32 * n_sets));
-    EGPU_CUDA(ctx, r.err.alloc(sizeof(HashErr)));
+    const size_t msg_cap = static_cast<size_t>(flat_bytes) + n + static_cast<size_t>(n_sets) * 128 + 64;
+    struct Want { DevBuf* b; size_t bytes; } wants[] = {
+        {&r.flat, static_cast<size_t>(flat_bytes)}, {&r.id_off, sizeof(long long) * (n + 1)},
+        {&r.set_off, sizeof(long long) * (n_sets + 1)}, {&r.key_a, 8 * n}, {&r.key_b, 8 * n}, {&r.set_a, 4 * n},
+        {&r.set_b, 4 * n}, {&r.len1, 4 * n}, {&r.pref, 8 * (n + 1)}, {&r.blk, 8 * ((n + 1023) / 1024 + 1)},
+        {&r.hist, 4 * 16 * static_cast<size_t>(tiles > 0 ? tiles : 1)}, {&r.msg_base, 8 * static_cast<size_t>(n_sets + 1)},
+        {&r.msg_len, 8 * static_cast<size_t>(n_sets)}, {&r.digest, 32 * static_cast<size_t>(n_sets)}, {&r.err, sizeof(HashErr)},
+        {&r.equal, sizeof(int) * static_cast<size_t>(n_sets)}, {&r.msg, need_digest ? msg_cap : 16}};
+    size_t total = 0;
+    for (const Want& w : wants) total += ((w.bytes ? w.bytes : 16) + 255) & ~static_cast<size_t>(255);
+    Arena arena(ctx);
+    EGPU_CUDA(ctx, arena.reserve(total));
+    for (const Want& w : wants) w.b->p = arena.take(w.bytes ? w.bytes : 16);
     EGPU_CUDA(ctx, cudaMemsetAsync(r.err.p, 0, sizeof(HashErr), s));
     if (flat_bytes) EGPU_CUDA(ctx, cudaMemcpyAsync(r.flat.p, ids_flat, flat_bytes, cudaMemcpyHostToDevice, s));
     EGPU_CUDA(ctx, cudaMemcpyAsync(r.id_off.p, id_offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
@@ -491,9 +508,7 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
         set_layout_kernel<<<1, 32, 0, s>>>(r.set_off.as<long long>(), n_sets, r.pref.as<unsigned long long>(),
                                            r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>());
         ctx->launches += 1;
-        // message buffer size: every ID contributes len + 1 <= 17 bytes, every set <= 127 bytes of padding
-        const size_t msg_cap = static_cast<size_t>(flat_bytes) + n + static_cast<size_t>(n_sets) * 128 + 64;
-        EGPU_CUDA(ctx, r.msg.alloc(msg_cap));
+        // (message buffer: every ID contributes len + 1 <= 17 bytes, every set <= 127 bytes of padding)
         if (n) {
             render_kernel<<<nb256, 256, 0, s>>>(ka, sa, n_ids, r.set_off.as<long long>(), r.pref.as<unsigned long long>(),
                                                 r.msg_base.as<unsigned long long>(), r.msg.as<unsigned char>());
@@ -567,7 +582,6 @@ int egpu_device_locate(egpu_ctx* ctx, const char* ids_flat, const int64_t* id_of
     if (rc != EGPU_OK) return rc;
     if (n_sets < 2) return EGPU_OK;
     cudaStream_t s = ctx->stream;
-    EGPU_CUDA(ctx, r.equal.alloc(sizeof(int) * n_sets));
     locate_init_kernel<<<static_cast<unsigned>((n_sets + 255) / 256), 256, 0, s>>>(r.equal.as<int>(), r.set_off.as<long long>(), n_sets);
     if (n_ids)
         locate_compare_kernel<<<static_cast<unsigned>((n_ids + 255) / 256), 256, 0, s>>>(r.sorted_key, r.sorted_set, n_ids,

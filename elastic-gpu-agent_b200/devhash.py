@@ -22,6 +22,32 @@ def _flatten(sets: list[list[str]]):
     return (bytes(flat), np.asarray(id_off, dtype=np.int64), np.asarray(set_off, dtype=np.int64))
 
 
+def flatten(sets: list[list[str]]):
+    """(ids_flat bytes, id_offsets int64[n_ids+1], set_offsets int64[n_sets+1]) — the C ABI's input layout."""
+    return _flatten(sets)
+
+
+def device_hashes_flat(alloc, flat: bytes, id_off: np.ndarray, set_off: np.ndarray):
+    """egpu_device_hash_batch on already flattened input; returns the 8-hex-digit hashes."""
+    n_sets = len(set_off) - 1
+    out = C.create_string_buffer(9 * n_sets)
+    rc = L.load().egpu_device_hash_batch(alloc.handle, C.c_char_p(flat), C.c_void_p(id_off.ctypes.data), len(id_off) - 1,
+                                         C.c_void_p(set_off.ctypes.data), n_sets, out, None)
+    if rc != L.OK:
+        raise L.EgpuError(rc, "egpu_device_hash_batch")
+    return [out.raw[9 * i:9 * i + 8].decode() for i in range(n_sets)]
+
+
+def locate_flat(alloc, flat: bytes, id_off: np.ndarray, set_off: np.ndarray) -> int:
+    """egpu_device_locate on flattened input (set 0 = request); candidate index or -1."""
+    m = C.c_int64(-1)
+    rc = L.load().egpu_device_locate(alloc.handle, C.c_char_p(flat), C.c_void_p(id_off.ctypes.data), len(id_off) - 1,
+                                     C.c_void_p(set_off.ctypes.data), len(set_off) - 1, C.byref(m))
+    if rc != L.OK:
+        raise L.EgpuError(rc, "egpu_device_locate")
+    return int(m.value) - 1 if m.value >= 1 else -1
+
+
 def device_hashes(alloc, sets: list[list[str]], want_digest: bool = False):
     """Device.Hash (8 hex digits) of every ID list; optionally the full SHA-256 digests too."""
     flat, id_off, set_off = _flatten(sets)

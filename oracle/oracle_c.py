@@ -134,3 +134,17 @@ def sha256(data: bytes) -> bytes:
     out = C.create_string_buffer(32)
     load().oracle_sha256(C.c_char_p(data), len(data), out)
     return out.raw
+
+
+def device_hash_prepared(ids):
+    """(callable, keepalive): the C call alone, for timing without Python marshalling."""
+    enc = [x.encode() for x in ids]
+    arr = (C.c_char_p * max(1, len(enc)))(*enc)
+    out = C.create_string_buffer(9)
+    fn = load().oracle_device_hash
+    n = len(enc)
+
+    def call():
+        fn(arr, n, out, None)
+        return out.value.decode()
+    return call, (enc, arr, out)
