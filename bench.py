@@ -184,8 +184,11 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO would print there
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL prints its
+    # version banner on the first communicator) is sent to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,6 +197,7 @@ def main():
     w = e.synth.workload(args.workload)
 
     if args.impl == "reference":
+        os.dup2(saved_stdout, 1)
         run_reference(args, w, e, rank, world)
         return
 
@@ -566,7 +570,10 @@ def main():
             "sweep": sweep,
             "next_rows": extra,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     alloc.close()
     if world > 1:
