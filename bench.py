@@ -56,6 +56,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scan kernel, from the
+    committed `ncu --set full` capture of this workload (profiles/r1_traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return float(json.load(open(p))[workload]["traffic"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed regions run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -414,6 +424,31 @@ def main():
     e2e = {"value": world * e2e_R * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * e2e_R,
            "d2h_bytes_per_step": 4 * e2e_R + 16 * D, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
            "api": "egpu_bestfit_batch (C ABI, pinned host buffers)"}
+    # same leg on the packed wire format (4 bytes in, 1 byte out per decision): PCIe, not the
+    # scan, bounds e2e, so this is the lever for callers that can produce packed requests
+    e2e_packed = None
+    if world == 1:
+        ph = []
+        for b in range(nhb):
+            pr = alloc.pinned_array(e2e_R, np.uint32)
+            pr[:] = alloc.pack_requests(host[b][0], host[b][1])
+            ph.append((pr, alloc.pinned_array(e2e_R, np.int8)))
+        for i in range(3):
+            alloc.bestfit_packed_raw(ph[i % nhb][0].ctypes.data, e2e_R, ph[i % nhb][1].ctypes.data, hdc.ctypes.data, hdm.ctypes.data)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            alloc.bestfit_packed_raw(ph[i % nhb][0].ctypes.data, e2e_R, ph[i % nhb][1].ctypes.data, hdc.ctypes.data, hdm.ctypes.data)
+        dtp = time.perf_counter() - t0
+        e2e_packed = {"value": e2e_R * e2e_steps / dtp, "unit": UNIT, "h2d_bytes_per_step": 4 * e2e_R,
+                      "d2h_bytes_per_step": e2e_R + 16 * D, "steps": e2e_steps, "ms_per_step": 1e3 * dtp / e2e_steps,
+                      "api": "egpu_bestfit_batch_packed (C ABI, pinned host buffers, 5 B per decision)"}
+        if rank == 0 and R <= (1 << 20):
+            from oracle import oracle_c
+            b = (e2e_steps - 1) % nhb
+            exp, *_ = oracle_c.snapshot(w["free_core"], w["free_mem"], host[b][0], host[b][1], oracle_c.max_threads())
+            e2e_packed["parity_vs_oracle"] = bool(np.array_equal(ph[b][1].astype(np.int32), exp))
+
     if rank == 0 and world == 1 and R <= (1 << 20):
         from oracle import oracle_c
         rc_h, rm_h = host[(e2e_steps - 1) % nhb][0], host[(e2e_steps - 1) % nhb][1]
@@ -560,9 +595,10 @@ def main():
                                   if use_peer else "eager launches + NCCL all-gather of demand vectors"),
                        "parallelism": f"request rows sharded over {world} GPU(s), table replicated"},
             "e2e": e2e,
+            "e2e_packed": e2e_packed,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "bestfit_sorted_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": ncu_traffic(args.workload), "kernel": "bestfit_sorted_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "avg_launch_us": per_launch_s * 1e6, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "clocks": clocks,

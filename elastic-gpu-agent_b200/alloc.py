@@ -115,6 +115,33 @@ class BestFitAllocator:
                                           C.c_void_p(p_dc), C.c_void_p(p_dm), 1 if commit else 0)
         self._check(rc, "egpu_bestfit_batch")
 
+    # -- packed wire format ----------------------------------------------------
+    @staticmethod
+    def pack_requests(req_core, req_mem) -> np.ndarray:
+        """EGPU_PACK_REQUEST over arrays; out-of-domain rows become EGPU_PACKED_INVALID."""
+        c = np.asarray(req_core, dtype=np.int64)
+        m = np.asarray(req_mem, dtype=np.int64)
+        ok = (c >= 0) & (c <= 127) & (m >= 0) & (m < (1 << 18))
+        return np.where(ok, (c << 18) | m, 0xFFFFFFFF).astype(np.uint32)
+
+    def bestfit_packed(self, req_packed, commit: bool = False):
+        """Returns (idx int8[R], delta_core int64[D], delta_mem int64[D])."""
+        p = np.ascontiguousarray(req_packed, dtype=np.uint32)
+        D = self._lib.egpu_table_size(self._h)
+        if D < 0:
+            raise L.EgpuError(D, "egpu_table_size")
+        idx = np.empty(p.size, dtype=np.int8)
+        dc = np.zeros(D, dtype=np.int64)
+        dm = np.zeros(D, dtype=np.int64)
+        rc = self._lib.egpu_bestfit_batch_packed(self._h, _ptr(p), p.size, _ptr(idx), _ptr(dc), _ptr(dm), 1 if commit else 0)
+        self._check(rc, "egpu_bestfit_batch_packed")
+        return idx, dc, dm
+
+    def bestfit_packed_raw(self, p_req: int, R: int, p_idx8: int, p_dc: int, p_dm: int, commit: bool = False):
+        rc = self._lib.egpu_bestfit_batch_packed(self._h, C.c_void_p(p_req), int(R), C.c_void_p(p_idx8), C.c_void_p(p_dc),
+                                                 C.c_void_p(p_dm), 1 if commit else 0)
+        self._check(rc, "egpu_bestfit_batch_packed")
+
     def host_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self._lib.egpu_host_alloc(self._h, C.byref(p), int(nbytes)), "egpu_host_alloc")

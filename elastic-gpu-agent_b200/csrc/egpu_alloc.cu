@@ -237,7 +237,7 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
                                    table_out, flags, slot_step);
 }
 
-template <int DT, int THREADS>
+template <int DT, int THREADS, int VEC>
 __global__ void __launch_bounds__(THREADS)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
@@ -255,17 +255,20 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     const long long stride = static_cast<long long>(gridDim.x) * THREADS;
     long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
 
-    // issue the first tile's loads before anything else: the request stream is
-    // the only HBM traffic that matters
-    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
-    bool has0 = v < nvec, has1 = (v + stride) < nvec;
-    if (has0) {
-        c0 = ld_stream_v4(req_core + 4 * v);
-        m0 = ld_stream_v4(req_mem + 4 * v);
-    }
-    if (has1) {
-        c1 = ld_stream_v4(req_core + 4 * (v + stride));
-        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
+    // issue the first trip's loads before anything else: the request stream is the only HBM
+    // traffic that matters.  VEC 128-bit vectors per array per trip, the next trip's VEC
+    // already in flight while this one is scored: 2 * VEC * 32 bytes per thread on the wire.
+    int4 c[VEC], m[VEC];
+    bool has[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) {
+        has[u] = (v + u * stride) < nvec;
+        c[u] = make_int4(0, 0, 0, 0);
+        m[u] = c[u];
+        if (has[u]) {
+            c[u] = ld_stream_v4(req_core + 4 * (v + u * stride));
+            m[u] = ld_stream_v4(req_mem + 4 * (v + u * stride));
+        }
     }
 
     // sorted table rows: uniform loads straight into registers, no barrier
@@ -298,24 +301,30 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         return r;
     };
 
-    while (has0) {
-        const long long vn = v + 2 * stride;
-        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
-        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
-        if (nhas0) {
-            nc0 = ld_stream_v4(req_core + 4 * vn);
-            nm0 = ld_stream_v4(req_mem + 4 * vn);
+    while (has[0]) {
+        const long long vn = v + VEC * stride;
+        int4 nc[VEC], nm[VEC];
+        bool nhas[VEC];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            nhas[u] = (vn + u * stride) < nvec;
+            nc[u] = make_int4(0, 0, 0, 0);
+            nm[u] = nc[u];
+            if (nhas[u]) {
+                nc[u] = ld_stream_v4(req_core + 4 * (vn + u * stride));
+                nm[u] = ld_stream_v4(req_mem + 4 * (vn + u * stride));
+            }
         }
-        if (nhas1) {
-            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
-            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
-        }
-        st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
+#pragma unroll
+        for (int u = 0; u < VEC; ++u)
+            if (has[u]) st_stream_v4(out_idx + 4 * (v + u * stride), decide4(c[u], m[u]));
         v = vn;
-        has0 = nhas0;
-        has1 = nhas1;
-        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            has[u] = nhas[u];
+            c[u] = nc[u];
+            m[u] = nm[u];
+        }
     }
     // ragged tail: R % 4 rows, scalar
     if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
@@ -324,6 +333,88 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     }
     snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
     if (late) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
+}
+
+// Packed wire format (include/egpu_alloc.h: egpu_bestfit_batch_packed): one uint32 per request
+// (core << 18 | mem, anything >= 2^25 = "no valid request") and one int8 per decision - 5 bytes
+// per decision instead of 12.  Same scan, same epilogue.
+template <int DT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bestfit_sorted_packed_kernel(DevState* __restrict__ st, const uint32_t* __restrict__ req, long long R,
+                             signed char* __restrict__ out_idx8, long long* __restrict__ delta_out,
+                             int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool late = (flags & kFlagLateWait) != 0;
+    if (!late) pdl_wait();
+    pdl_trigger();
+
+    // A warp takes chunks of 512 requests (2 KiB in, 512 B out): four fully coalesced 128-bit
+    // loads per lane (lane-contiguous, 512 B per instruction) and four coalesced 32-bit stores.
+    const long long nchunk = R >> 9;
+    const long long wstride = static_cast<long long>(gridDim.x) * (THREADS / 32);
+    long long ch = static_cast<long long>(blockIdx.x) * (THREADS / 32) + warp;
+    uint4 p[4];
+    bool has = ch < nchunk;
+    auto load_chunk = [&](long long ci, uint4 (&dst)[4]) {
+        const uint4* src = reinterpret_cast<const uint4*>(req) + 128 * ci + lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int4 t = ld_stream_v4(reinterpret_cast<const int32_t*>(src + 32 * u));
+            dst[u] = make_uint4(t.x, t.y, t.z, t.w);
+        }
+    };
+    if (has) load_chunk(ch, p);
+
+    const int D = st->D;
+    uint32_t K[DT];
+#pragma unroll
+    for (int j = 0; j < DT; j += 4) {
+        const uint4 k4 = *reinterpret_cast<const uint4*>(&st->sorted_k[j]);
+        K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
+    }
+    const uint32_t gx = st->cand_xor, gm = st->cand_mask;
+    int32_t* tile = s.sDevTile[warp];
+    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
+    hist_zero<DT, THREADS>(s, warp, lane);
+    __syncwarp();
+
+    auto decide = [&](uint32_t pw) -> uint32_t {
+        // core << 18 | mem  ->  core << 24 | mem << 5; out-of-format words fail every guard
+        const uint32_t q = (pw >> 25) ? (127u << 24) : (((pw & ~0x3FFFFu) << 6) | ((pw & 0x3FFFFu) << 5));
+        const uint32_t best = first_feasible<DT>(K, q, gx, gm);
+        const int32_t idx = tile[best];
+        hist_add<DT, THREADS>(s, warp, lane, idx, static_cast<int32_t>((pw >> 18) & 127u), static_cast<int32_t>(pw & 0x3FFFFu));
+        return static_cast<uint32_t>(idx) & 0xffu;
+    };
+    auto decide4 = [&](const uint4& v) -> uint32_t {
+        return decide(v.x) | (decide(v.y) << 8) | (decide(v.z) << 16) | (decide(v.w) << 24);
+    };
+    while (has) {
+        const long long cn = ch + wstride;
+        const bool nhas = cn < nchunk;
+        uint4 np[4];
+        if (nhas) load_chunk(cn, np);
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(out_idx8) + 128 * ch + lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t r4 = decide4(p[u]);
+            asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(out32 + 32 * u), "r"(r4) : "memory");
+        }
+        ch = cn;
+        has = nhas;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = np[u];
+    }
+    // ragged tail: R % 512 rows, scalar, spread over the first CTA
+    if (blockIdx.x == 0) {
+        for (long long r = (nchunk << 9) + tid; r < R; r += THREADS) out_idx8[r] = static_cast<signed char>(decide(req[r]));
+    }
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
+    if (late) pdl_wait();
 }
 
 // The north-star's literal formulation: every (device, request) pair is scored
@@ -755,7 +846,8 @@ __global__ void synth_requests_kernel(int dist, unsigned long long seed, long lo
 }
 
 // =============================================================================
-// Sequential mode: one warp, lane = device (two per lane when D > 32)
+// Sequential mode: one warp.  D <= 8: table in registers (replay8_kernel, below the general
+// one); otherwise lane = device (two per lane when D > 32)
 // =============================================================================
 //
 // Request k sees the table after k-1: a serial dependence chain, so there is no
@@ -845,6 +937,105 @@ replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const
     resort_table_cta(st, D, sFc, sFm, sPosDev, lane);
 }
 
+// Sequential mode for D <= 8: the whole table lives in the registers of every lane as packed
+// compare words (guard | free_core | guard | free_mem | device).  K[d] - Q is at once the
+// feasibility test (both guards survive), the ordering key of the spec ((lc, lm, d) with the
+// guards as constant top bits) and the updated table word of the chosen device — so an ALLOC
+// is 8 subtracts, 8 guard tests, a 3-input-min tree and 8 selects, with no cross-lane
+// traffic on the dependence chain.  All lanes compute the same thing; lane 0 keeps `live`
+// and the outputs.  Events are held 32 at a time in registers (lane j = event j of the chunk),
+// broadcast with shuffles; the next chunk is prefetched while the current one is processed.
+__global__ void __launch_bounds__(32)
+replay8_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const int32_t* __restrict__ ev_a,
+               const int32_t* __restrict__ ev_b, long long E, int32_t* __restrict__ out_idx,
+               signed char* __restrict__ live_global) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    signed char* live = (E <= kReplaySmemEvents) ? reinterpret_cast<signed char*>(smem_raw) : live_global;
+    const int lane = threadIdx.x;
+    const int D = st->D;
+    uint32_t K[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+        K[d] = d < D ? (pack_table_word(st->free_core[d], st->free_mem[d]) | static_cast<uint32_t>(d)) : kPadWord;
+
+    auto fetch = [&](long long i, int32_t& k, uint32_t& q, uint32_t& qt, int32_t& t) {
+        k = -1; q = 0; qt = 0; t = -1;
+        if (i < E) {
+            k = kind[i];
+            const int32_t a = ev_a[i], b = ev_b[i];
+            q = pack_request_word(a, b);
+            if (k == 1 && a >= 0 && a < i && kind[a] == 0) {  // FREE of an earlier ALLOC: fetch its request now
+                t = a;
+                qt = pack_request_word(ev_a[a], ev_b[a]);
+            }
+        }
+    };
+    int32_t nk; uint32_t nq, nqt; int32_t nt;
+    fetch(lane, nk, nq, nqt, nt);
+    for (long long base = 0; base < E; base += 32) {
+        // this chunk's events stay in registers (lane j holds event base + j) and are broadcast
+        // with shuffles, which do not sit on the dependence chain; `live` is lane 0's alone
+        const int32_t ck = nk, ct = nt;
+        const uint32_t cq = nq, cqt = nqt;
+        fetch(base + 32 + lane, nk, nq, nqt, nt);  // prefetch the next chunk
+        const int n = (E - base) < 32 ? static_cast<int>(E - base) : 32;
+        int32_t my_out = -1;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const int32_t kj = __shfl_sync(0xffffffffu, ck, j);
+            const uint32_t q = __shfl_sync(0xffffffffu, cq, j);
+            int32_t res = -1;
+            if (kj == 0) {
+                uint32_t w[8], key[8];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    w[d] = K[d] - q;
+                    key[d] = ((w[d] & kGuards) == kGuards) ? w[d] : 0xFFFFFFFFu;
+                }
+                const uint32_t best = __vimin3_u32(__vimin3_u32(key[0], key[1], key[2]), __vimin3_u32(key[3], key[4], key[5]),
+                                                   min(key[6], key[7]));
+                if (best != 0xFFFFFFFFu) {
+                    res = static_cast<int32_t>(best & 31u);
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) K[d] = (w[d] == best) ? w[d] : K[d];
+                }
+                if (lane == 0) live[base + j] = static_cast<signed char>(res);
+            } else {
+                const int32_t t = __shfl_sync(0xffffffffu, ct, j);
+                const uint32_t qt = __shfl_sync(0xffffffffu, cqt, j);
+                int32_t dev = -1;
+                if (lane == 0) {
+                    live[base + j] = -1;
+                    if (t >= 0) {
+                        dev = live[t];
+                        live[t] = -1;
+                    }
+                }
+                dev = __shfl_sync(0xffffffffu, dev, 0);
+                if (dev >= 0) {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) K[d] = (d == dev) ? K[d] + qt : K[d];
+                    res = dev;
+                }
+            }
+            if (lane == j) my_out = res;
+        }
+        if (base + lane < E) out_idx[base + lane] = my_out;
+    }
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    if (lane < D) {
+        uint32_t k = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) k = (d == lane) ? K[d] : k;
+        const int32_t fc = static_cast<int32_t>((k >> 24) & 0x7Fu), fm = static_cast<int32_t>((k >> 5) & 0x3FFFFu);
+        st->free_core[lane] = fc;
+        st->free_mem[lane] = fm;
+        sFc[lane] = fc;
+        sFm[lane] = fm;
+    }
+    resort_table_cta(st, D, sFc, sFm, sPosDev, lane);
+}
+
 }  // namespace egpu
 
 // =============================================================================
@@ -859,7 +1050,7 @@ namespace {
 template <int DT, int THREADS>
 SnapLaunch make_launch(bool grid_variant) {
     SnapLaunch l;
-    l.fn = grid_variant ? bestfit_grid_kernel<DT, THREADS> : bestfit_sorted_kernel<DT, THREADS>;
+    l.fn = grid_variant ? bestfit_grid_kernel<DT, THREADS> : bestfit_sorted_kernel<DT, THREADS, 2>;
     l.threads = THREADS;
     l.smem = sizeof(SnapSmem<DT, THREADS>);
     l.ctas_per_sm = 0;
@@ -903,7 +1094,9 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
-    SnapLaunch& l = ctx->snap[grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
+    // D <= 8 on a pipelined stream: the deeper-prefetch build (4 vectors per array per trip)
+    const bool vec4 = !grid_variant && !lut_variant && bucket == 0 && ctx->vec == 4 && (user_flags & EGPU_F_INPUTS_READY);
+    SnapLaunch& l = ctx->snap[vec4 ? 3 : grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
     if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
         int per_sm = 0;
         if (lut_variant) {
@@ -917,6 +1110,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
             l = pick_launch(ctx->D, grid_variant);
+            if (vec4) l.fn = bestfit_sorted_kernel<8, 256, 4>;
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
         }
@@ -1008,6 +1202,53 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     return EGPU_OK;
 }
 
+using PackedKernel = void (*)(DevState*, const uint32_t*, long long, signed char*, long long*, int32_t*, int, unsigned long long);
+
+// Packed-format scan: always a fully ordered launch (it serves the synchronous host path).
+int launch_packed(egpu_ctx* ctx, const uint32_t* d_req, int64_t R, signed char* d_idx8, long long* d_delta,
+                  int32_t* d_table_out, int user_flags, cudaStream_t s, int rows_per_thread) {
+    const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
+    static const PackedKernel fns[4] = {bestfit_sorted_packed_kernel<8, 256>, bestfit_sorted_packed_kernel<16, 256>,
+                                        bestfit_sorted_packed_kernel<32, 256>, bestfit_sorted_packed_kernel<64, 128>};
+    static const int threads[4] = {256, 256, 256, 128};
+    static const size_t smem[4] = {sizeof(SnapSmem<8, 256>), sizeof(SnapSmem<16, 256>), sizeof(SnapSmem<32, 256>),
+                                   sizeof(SnapSmem<64, 128>)};
+    int& per_sm = ctx->packed_ctas_per_sm[bucket];
+    if (per_sm == 0) {
+        EGPU_CUDA(ctx, cudaFuncSetAttribute(fns[bucket], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem[bucket])));
+        int n = 0;
+        EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[bucket], threads[bucket], smem[bucket]));
+        per_sm = n < 1 ? 1 : n;
+    }
+    const int64_t nchunk = R >> 9;  // 512 requests per warp trip
+    const int64_t per_cta = static_cast<int64_t>(threads[bucket] / 32) * ((rows_per_thread + 15) / 16);
+    int64_t want = (nchunk + per_cta - 1) / per_cta;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    if (R / (want * threads[bucket]) + 16 >= (1ll << 19)) return EGPU_ERR_INVALID;
+    const int flags = kFlagFinalize | ((user_flags & EGPU_F_COMMIT) ? kFlagCommit : 0);
+    const unsigned long long slot = ctx->seq % kEpiSlots;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(want));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads[bucket]));
+    cfg.dynamicSmemBytes = smem[bucket];
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, fns[bucket], ctx->d_state, d_req, static_cast<long long>(R), d_idx8, d_delta,
+                                      d_table_out, flags, slot));
+    ctx->launches += 1;
+    ctx->seq += 1;
+    ctx->group_len = 0;
+    ctx->prev_is_scan = false;  // the int32 scans do not pipeline behind this one
+    if (flags & kFlagCommit) ctx->lut_dirty = true;
+    return EGPU_OK;
+}
+
 int ensure_staging(egpu_ctx* ctx, int64_t rows) {
     if (rows <= ctx->d_cap_rows) return EGPU_OK;
     int64_t cap = ctx->d_cap_rows ? ctx->d_cap_rows : 1024;
@@ -1077,6 +1318,8 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         ctx->sm_count = prop.multiProcessorCount;
         if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
+        if (const char* e = std::getenv("EGPU_REPLAY_GENERAL")) ctx->replay_general = std::atoi(e) != 0;
+        if (const char* e = std::getenv("EGPU_VEC")) ctx->vec = std::atoi(e) == 4 ? 4 : 2;
         if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
             const int v = std::atoi(e);
             ctx->lut_share = (v == 1 || v == 2 || v == 8) ? v : 4;
@@ -1375,6 +1618,51 @@ int64_t egpu_peer_last_timeout(egpu_ctx* ctx) {
     return static_cast<int64_t>(v);
 }
 
+int egpu_bestfit_batch_packed_dev(egpu_ctx* ctx, const uint32_t* d_req_packed, int64_t R, int8_t* d_out_idx8,
+                                  int64_t* d_delta, int32_t* d_table_out, int flags, void* stream) {
+    if (!ctx || R < 0) return EGPU_ERR_INVALID;
+    if (R > 0 && (!d_req_packed || !d_out_idx8)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_packed) || !aligned16(d_out_idx8)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_packed(ctx, d_req_packed, R, reinterpret_cast<signed char*>(d_out_idx8), reinterpret_cast<long long*>(d_delta),
+                         d_table_out, flags, s, 16);
+}
+
+int egpu_bestfit_batch_packed(egpu_ctx* ctx, const uint32_t* req_packed, int64_t R, int8_t* out_idx8,
+                              int64_t* out_delta_core, int64_t* out_delta_mem, int commit) {
+    if (!ctx || R < 0) return EGPU_ERR_INVALID;
+    if (R > 0 && (!req_packed || !out_idx8)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const int D = ctx->D;
+    int rc;
+    const uint32_t* zr = R > 0 ? static_cast<const uint32_t*>(mapped_alias(req_packed)) : nullptr;
+    signed char* zi = R > 0 ? static_cast<signed char*>(mapped_alias(out_idx8)) : nullptr;
+    if (zr && zi && aligned16(zr) && aligned16(zi) && !ctx->no_zero_copy) {  // zero-copy across PCIe, see egpu_bestfit_batch
+        rc = launch_packed(ctx, zr, R, zi, ctx->h_delta_dev, nullptr, commit ? EGPU_F_COMMIT : 0, s, 128);
+        if (rc != EGPU_OK) return rc;
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    } else {
+        rc = ensure_staging(ctx, R > 0 ? R : 1);  // d_req_core holds the packed words, d_idx the bytes
+        if (rc != EGPU_OK) return rc;
+        if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_packed, sizeof(uint32_t) * R, cudaMemcpyHostToDevice, s));
+        rc = launch_packed(ctx, reinterpret_cast<const uint32_t*>(ctx->d_req_core), R, reinterpret_cast<signed char*>(ctx->d_idx),
+                           ctx->d_delta, nullptr, commit ? EGPU_F_COMMIT : 0, s, 16);
+        if (rc != EGPU_OK) return rc;
+        if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx8, ctx->d_idx, static_cast<size_t>(R), cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    if (out_delta_core) std::memcpy(out_delta_core, ctx->h_delta, sizeof(int64_t) * D);
+    if (out_delta_mem) std::memcpy(out_delta_mem, ctx->h_delta + D, sizeof(int64_t) * D);
+    return EGPU_OK;
+}
+
 int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G, int32_t* d_table_out,
                                 int commit, void* stream) {
     if (!ctx || !d_deltas || G < 1) return EGPU_ERR_INVALID;
@@ -1430,6 +1718,8 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
             smem = static_cast<size_t>((E + 15) & ~15ll);
             EGPU_CUDA(ctx, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 kReplaySmemEvents));
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                kReplaySmemEvents));
         } else if (E > ctx->d_live_cap) {
             cudaFree(ctx->d_live);
             ctx->d_live = nullptr;
@@ -1442,7 +1732,10 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
         EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
         ctx->prev_is_scan = false;
         ctx->lut_dirty = true;
-        replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
+        if (ctx->D <= 8 && !ctx->replay_general)
+            replay8_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
+        else
+            replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
         EGPU_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, d_out, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));

@@ -137,6 +137,18 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core,
                        int64_t* out_delta_core, int64_t* out_delta_mem,
                        int commit);
 
+/* Packed wire format, for callers bound by PCIe rather than by the scan: 5 bytes per decision
+ * instead of 12.  req_packed[r] = EGPU_PACK_REQUEST(core, mem) (core in 0..127, mem in
+ * 0..2^18-1; any word >= 2^25, e.g. EGPU_PACKED_INVALID, is an infeasible request);
+ * out_idx8[r] = device index 0..63 or -1.  Everything else as egpu_bestfit_batch. */
+#define EGPU_PACK_REQUEST(core, mem) (((uint32_t)(core) << 18) | (uint32_t)(mem))
+#define EGPU_PACKED_INVALID 0xFFFFFFFFu
+int egpu_bestfit_batch_packed(egpu_ctx* ctx, const uint32_t* req_packed, int64_t R, int8_t* out_idx8,
+                              int64_t* out_delta_core, int64_t* out_delta_mem, int commit);
+int egpu_bestfit_batch_packed_dev(egpu_ctx* ctx, const uint32_t* d_req_packed, int64_t R,
+                                  int8_t* d_out_idx8, int64_t* d_delta, int32_t* d_table_out,
+                                  int flags, void* stream);
+
 /* Pinned host memory for callers that want zero staging copies. */
 int  egpu_host_alloc(egpu_ctx* ctx, void** out, int64_t bytes);
 void egpu_host_free(egpu_ctx* ctx, void* p);

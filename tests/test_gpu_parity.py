@@ -128,6 +128,35 @@ def test_zero_copy_pinned_buffers(D, dist, alloc, oracle_c, egpu):
         alloc.host_free(a.ctypes.data)
 
 
+@pytest.mark.parametrize("D", [1, 8, 9, 33, 64])
+def test_packed_wire_format(D, alloc, oracle_c, egpu):
+    """5-byte-per-decision format: same decisions as the int32 arrays, staged and zero-copy."""
+    rng = np.random.default_rng(2000 + D)
+    fc = rng.integers(0, 101, D).astype(np.int32)
+    fm = rng.integers(0, 1 << 18, D).astype(np.int32)
+    for R in (0, 1, 15, 16, 17, 70_001):
+        rc = rng.integers(-1, 130, R).astype(np.int32)
+        rm = rng.integers(-1, (1 << 18) + 2, R).astype(np.int32)
+        rm[::2] = rng.integers(0, 8192, rm[::2].size)
+        packed = alloc.pack_requests(rc, rm)
+        # what the packed format can express: out-of-domain rows are "invalid" = infeasible, as in the spec
+        o_idx, o_dc, o_dm, _ = oracle_c.snapshot(fc, fm, rc, rm, 4)
+        alloc.set_table(fc, fm)
+        idx, dc, dm = alloc.bestfit_packed(packed)
+        assert np.array_equal(idx.astype(np.int32), o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+        if R:
+            pr = alloc.pinned_array(R, np.uint32)
+            pi = alloc.pinned_array(R + 16, np.int8)
+            hdc, hdm = alloc.pinned_array(D, np.int64), alloc.pinned_array(D, np.int64)
+            pr[:] = packed
+            pi[:] = 55
+            alloc.bestfit_packed_raw(pr.ctypes.data, R, pi.ctypes.data, hdc.ctypes.data, hdm.ctypes.data)
+            assert np.array_equal(pi[:R].astype(np.int32), o_idx) and (pi[R:] == 55).all()
+            assert np.array_equal(hdc, o_dc) and np.array_equal(hdm, o_dm)
+            for a in (pr, pi, hdc, hdm):
+                alloc.host_free(a.ctypes.data)
+
+
 def test_ties_pick_lowest_index_everywhere(alloc):
     for D in (8, 64):
         alloc.set_table([100] * D, [1000] * D)
@@ -190,6 +219,24 @@ def test_replay_random(D, E, alloc, oracle_c):
     assert np.array_equal(idx, o_idx)
     g_c, g_m, _ = alloc.table()
     assert np.array_equal(g_c, o_fc) and np.array_equal(g_m, o_fm)
+
+
+def test_replay_both_kernels_agree_for_small_tables(oracle_c, egpu, monkeypatch):
+    """D <= 8 takes the table-in-registers kernel; EGPU_REPLAY_GENERAL=1 forces the
+    lane = device kernel.  Both must match the oracle on the same churn stream."""
+    kind, a, b = egpu.synth.churn_events(9, 50_000)
+    for D in (1, 3, 8):
+        fc, fm = egpu.synth.table_fragmented(40 + D, D)
+        fc = np.maximum(fc, 30)
+        o_idx, o_fc, o_fm = oracle_c.replay(fc, fm, kind, a, b)
+        for general in ("0", "1"):
+            monkeypatch.setenv("EGPU_REPLAY_GENERAL", general)
+            with egpu.BestFitAllocator(0) as al:
+                al.set_table(fc, fm)
+                idx = al.replay(kind, a, b)
+                g_c, g_m, _ = al.table()
+            assert np.array_equal(idx, o_idx), (D, general)
+            assert np.array_equal(g_c, o_fc) and np.array_equal(g_m, o_fm)
 
 
 def test_device_synth_matches_numpy(alloc, egpu):
