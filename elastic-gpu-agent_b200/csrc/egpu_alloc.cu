@@ -553,7 +553,7 @@ struct LutSmem {
     unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
     int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     int sLast;
-    unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];
+    alignas(16) unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];  // zeroed with 128-bit stores
 };
 
 template <int THREADS, int SHARE>
@@ -594,9 +594,10 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
     }
     const int D = st->D;
-    if (phase == 0) {
-#pragma unroll 1
-        for (int d = 0; d <= kMaxD; ++d) sm.hist[warp][d][col] = 0ull;
+    {   // zero this warp's accumulators with 128-bit stores
+        uint4* hz = reinterpret_cast<uint4*>(&sm.hist[warp][0][0]);
+        constexpr int n16 = (kMaxD + 1) * LW * 8 / 16;
+        for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     const DevLut& L = sm.lut;
@@ -612,18 +613,41 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         for (uint32_t i = 1; i < n; ++i) rank += (L.v[lo + i] < m);  // rare: several distinct fm in one 64 MiB bucket
         return static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
     };
-    auto accumulate = [&](int32_t idx, int32_t core, int32_t mem) {
-        const unsigned long long val = (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-                                       static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-        unsigned long long* h = &sm.hist[warp][idx + 1][col];
-        if (SHARE == 1) {
-            *h += val;
-        } else {
+    // Demand sums for the four requests of one vector at once.  Requests of this thread that
+    // chose the same device are merged first (the later one is redirected to the dummy row
+    // with nothing to add), so the four read-modify-writes are independent and can be issued
+    // as four loads, four adds, four stores per phase instead of four dependent chains.
+    auto accumulate4 = [&](const int4& r, const int4& c, const int4& m) {
+        auto val = [](int32_t core, int32_t mem) {
+            return (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
+                   static_cast<unsigned long long>(static_cast<uint32_t>(mem));
+        };
+        int32_t i0 = r.x, i1 = r.y, i2 = r.z, i3 = r.w;
+        unsigned long long v0 = val(c.x, m.x), v1 = val(c.y, m.y), v2 = val(c.z, m.z), v3 = val(c.w, m.w);
+        if (i0 < 0) v0 = 0;  // infeasible rows carry out-of-domain values: keep the dummy row harmless
+        if (i1 < 0) v1 = 0;
+        if (i2 < 0) v2 = 0;
+        if (i3 < 0) v3 = 0;
+        if (i3 == i2) { v2 += v3; v3 = 0; i3 = -1; }
+        if (i3 == i1) { v1 += v3; v3 = 0; i3 = -1; }
+        if (i3 == i0) { v0 += v3; v3 = 0; i3 = -1; }
+        if (i2 == i1) { v1 += v2; v2 = 0; i2 = -1; }
+        if (i2 == i0) { v0 += v2; v2 = 0; i2 = -1; }
+        if (i1 == i0) { v0 += v1; v1 = 0; i1 = -1; }
+        unsigned long long* h0 = &sm.hist[warp][i0 + 1][col];
+        unsigned long long* h1 = &sm.hist[warp][i1 + 1][col];
+        unsigned long long* h2 = &sm.hist[warp][i2 + 1][col];
+        unsigned long long* h3 = &sm.hist[warp][i3 + 1][col];
 #pragma unroll
-            for (int p = 0; p < SHARE; ++p) {
-                if (phase == p) *h += val;
-                __syncwarp();
+        for (int p = 0; p < SHARE; ++p) {
+            if (SHARE == 1 || phase == p) {
+                const unsigned long long a0 = *h0, a1 = *h1, a2 = *h2, a3 = *h3;
+                *h0 = a0 + v0;
+                *h1 = a1 + v1;
+                *h2 = a2 + v2;
+                *h3 = a3 + v3;  // several redirected requests may all hit the dummy row: its content is never read
             }
+            if (SHARE > 1) __syncwarp();
         }
     };
     auto decide4 = [&](const int4& c, const int4& m) -> int4 {
@@ -632,10 +656,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         r.y = lookup(c.y, m.y);
         r.z = lookup(c.z, m.z);
         r.w = lookup(c.w, m.w);
-        accumulate(r.x, c.x, m.x);
-        accumulate(r.y, c.y, m.y);
-        accumulate(r.z, c.z, m.z);
-        accumulate(r.w, c.w, m.w);
+        accumulate4(r, c, m);
         return r;
     };
     while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: accumulate() synchronises the warp
@@ -667,23 +688,26 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         const long long r = (nvec << 2) + lane;
         const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
         const int32_t idx = lookup(c, m);
-        accumulate(idx, c, m);
+        accumulate4(make_int4(idx, -1, -1, -1), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0));
         if (mine) out_idx[r] = idx;
     }
-    // warp sums -> sWarpAcc (same layout as the register scan's epilogue)
+    // warp sums -> sWarpAcc, transposed: lane L adds up the LW columns of devices L and L + 32
+    // (rotated start column: conflict-free), instead of three warp reductions per device
     __syncwarp();
-    for (int d = 0; d < D; ++d) {
-        const unsigned long long hv = phase == 0 ? sm.hist[warp][d + 1][col] : 0ull;
-        const uint32_t c = static_cast<uint32_t>(hv >> kAccShift);
-        const uint32_t ml = static_cast<uint32_t>(hv) & 0x7FFFFu;
-        const uint32_t mh = static_cast<uint32_t>(hv >> 19) & 0x7FFFFu;
-        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
-        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
-        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
-        if (lane == 0) {
-            sm.sWarpAcc[warp][d] = sc;
-            sm.sWarpAcc[warp][kMaxD + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int d = lane + 32 * half;
+        unsigned long long sc = 0, smem_sum = 0;
+        if (d < D) {
+#pragma unroll 4
+            for (int k = 0; k < LW; ++k) {
+                const unsigned long long hv = sm.hist[warp][d + 1][(k + lane) & (LW - 1)];
+                sc += hv >> kAccShift;
+                smem_sum += hv & ((1ull << kAccShift) - 1ull);
+            }
         }
+        sm.sWarpAcc[warp][d] = sc;
+        sm.sWarpAcc[warp][kMaxD + d] = smem_sum;
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
@@ -1101,11 +1125,17 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         int per_sm = 0;
         if (lut_variant) {
             const int share = ctx->lut_share;
-            l.lut_fn = share == 1 ? bestfit_lut_kernel<128, 1> : share == 2 ? bestfit_lut_kernel<128, 2>
-                       : share == 4 ? bestfit_lut_kernel<128, 4> : bestfit_lut_kernel<128, 8>;
-            l.threads = 128;
-            l.smem = share == 1 ? sizeof(LutSmem<128, 1>) : share == 2 ? sizeof(LutSmem<128, 2>)
-                     : share == 4 ? sizeof(LutSmem<128, 4>) : sizeof(LutSmem<128, 8>);
+            if (ctx->lut_threads == 256) {
+                l.lut_fn = share == 2 ? bestfit_lut_kernel<256, 2> : share == 8 ? bestfit_lut_kernel<256, 8> : bestfit_lut_kernel<256, 4>;
+                l.threads = 256;
+                l.smem = share == 2 ? sizeof(LutSmem<256, 2>) : share == 8 ? sizeof(LutSmem<256, 8>) : sizeof(LutSmem<256, 4>);
+            } else {
+                l.lut_fn = share == 1 ? bestfit_lut_kernel<128, 1> : share == 2 ? bestfit_lut_kernel<128, 2>
+                           : share == 4 ? bestfit_lut_kernel<128, 4> : bestfit_lut_kernel<128, 8>;
+                l.threads = 128;
+                l.smem = share == 1 ? sizeof(LutSmem<128, 1>) : share == 2 ? sizeof(LutSmem<128, 2>)
+                         : share == 4 ? sizeof(LutSmem<128, 4>) : sizeof(LutSmem<128, 8>);
+            }
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
@@ -1159,7 +1189,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
     int rpt = 8;
-    if (user_flags & EGPU_F_INPUTS_READY) rpt = lut_variant ? 96 : (ctx->D <= 16 ? 48 : 8);  // measured, scripts/tune_*.sh
+    if (user_flags & EGPU_F_INPUTS_READY) rpt = (lut_variant || ctx->D <= 16) ? 48 : 8;  // measured, scripts/tune_*.sh
     else if (lut_variant) rpt = 32;  // the lookup scan has a 13 KB per-CTA table tile to amortise
     if (rpt_hint > 0) rpt = rpt_hint;
     if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
@@ -1320,6 +1350,7 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
         if (const char* e = std::getenv("EGPU_REPLAY_GENERAL")) ctx->replay_general = std::atoi(e) != 0;
         if (const char* e = std::getenv("EGPU_VEC")) ctx->vec = std::atoi(e) == 4 ? 4 : 2;
+        if (const char* e = std::getenv("EGPU_LUT_THREADS")) ctx->lut_threads = std::atoi(e) == 128 ? 128 : 256;
         if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
             const int v = std::atoi(e);
             ctx->lut_share = (v == 1 || v == 2 || v == 8) ? v : 4;
@@ -1369,7 +1400,6 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
     cudaFree(ctx->d_idx);
     cudaFree(ctx->d_delta);
     cudaFree(ctx->d_table_out);
-    cudaFree(ctx->d_live);
     if (ctx->h_delta) cudaFreeHost(ctx->h_delta);
     if (ctx->h_table) cudaFreeHost(ctx->h_table);
     (void)cudaGetLastError();
@@ -1705,48 +1735,48 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
     if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
     if (E == 0) return EGPU_OK;
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
-    // staging: kind -> d_req_core?  three inputs + one output: use own buffers
-    int32_t *d_kind = nullptr, *d_a = nullptr, *d_b = nullptr, *d_out = nullptr;
+    // staging comes from the context's grow-only arena (three inputs, one output, the `live`
+    // map when it does not fit in shared memory): no cudaMalloc/cudaFree on the call path
     cudaStream_t s = ctx->stream;
-    int rc = [&]() -> int {
-        EGPU_CUDA(ctx, cudaMalloc(&d_kind, sizeof(int32_t) * E));
-        EGPU_CUDA(ctx, cudaMalloc(&d_a, sizeof(int32_t) * E));
-        EGPU_CUDA(ctx, cudaMalloc(&d_b, sizeof(int32_t) * E));
-        EGPU_CUDA(ctx, cudaMalloc(&d_out, sizeof(int32_t) * E));
-        size_t smem = 0;
-        if (E <= kReplaySmemEvents) {
-            smem = static_cast<size_t>((E + 15) & ~15ll);
-            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                kReplaySmemEvents));
-            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                kReplaySmemEvents));
-        } else if (E > ctx->d_live_cap) {
-            cudaFree(ctx->d_live);
-            ctx->d_live = nullptr;
-            ctx->d_live_cap = 0;
-            EGPU_CUDA(ctx, cudaMalloc(&ctx->d_live, static_cast<size_t>(E)));
-            ctx->d_live_cap = E;
+    const size_t ebytes = (sizeof(int32_t) * static_cast<size_t>(E) + 255) & ~static_cast<size_t>(255);
+    const size_t lbytes = E > kReplaySmemEvents ? ((static_cast<size_t>(E) + 255) & ~static_cast<size_t>(255)) : 0;
+    const size_t need = 4 * ebytes + lbytes;
+    if (need > ctx->arena_cap) {
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->arena, need + need / 4));
+        ctx->arena_cap = need + need / 4;
+    }
+    char* base = static_cast<char*>(ctx->arena);
+    int32_t* d_kind = reinterpret_cast<int32_t*>(base);
+    int32_t* d_a = reinterpret_cast<int32_t*>(base + ebytes);
+    int32_t* d_b = reinterpret_cast<int32_t*>(base + 2 * ebytes);
+    int32_t* d_out = reinterpret_cast<int32_t*>(base + 3 * ebytes);
+    signed char* d_live = lbytes ? reinterpret_cast<signed char*>(base + 4 * ebytes) : nullptr;
+    size_t smem = 0;
+    if (E <= kReplaySmemEvents) {
+        smem = static_cast<size_t>((E + 15) & ~15ll);
+        if (!ctx->replay_configured) {
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemEvents));
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemEvents));
+            ctx->replay_configured = true;
         }
-        EGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
-        EGPU_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
-        EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
-        ctx->prev_is_scan = false;
-        ctx->lut_dirty = true;
-        if (ctx->D <= 8 && !ctx->replay_general)
-            replay8_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
-        else
-            replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, ctx->d_live);
-        EGPU_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 1;
-        EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, d_out, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
-        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
-        return EGPU_OK;
-    }();
-    cudaFree(d_kind);
-    cudaFree(d_a);
-    cudaFree(d_b);
-    cudaFree(d_out);
-    return rc;
+    }
+    EGPU_CUDA(ctx, cudaMemcpyAsync(d_kind, kind, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    ctx->prev_is_scan = false;
+    ctx->lut_dirty = true;
+    if (ctx->D <= 8 && !ctx->replay_general)
+        replay8_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, d_live);
+    else
+        replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, d_live);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, d_out, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    return EGPU_OK;
 }
 
 }  // extern "C"

@@ -54,8 +54,7 @@ struct egpu_ctx {
     long long* h_delta_dev = nullptr; // its device-visible alias
     bool no_zero_copy = false;        // EGPU_NO_ZERO_COPY=1: always stage through HBM
     int32_t* h_table = nullptr;       // pinned int32[3*64]
-    signed char* d_live = nullptr;
-    int64_t d_live_cap = 0;
+    bool replay_configured = false;   // shared-memory opt-in of the replay kernels done
     // bookkeeping for programmatic dependent launch (see launch_snapshot)
     bool prev_is_scan = false;        // the last kernel this context launched was a snapshot scan ...
     bool prev_changes_table = false;  // ... and it may rewrite the table (commit)
@@ -69,6 +68,7 @@ struct egpu_ctx {
     int packed_ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the packed-format scan per D bucket, 0 = not asked yet
     int vec = 2;                      // 128-bit vectors per array per trip for D <= 8 (EGPU_VEC = 2 | 4)
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
+    int lut_threads = 256;            // CTA size of the lookup scan (EGPU_LUT_THREADS = 128 | 256)
     int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
     // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
     void* arena = nullptr;

@@ -6,4 +6,4 @@ try:
 except Exception as ex: print(sys.argv[1], "FAILED", ex, open("gpurun_out/b.err").read()[-800:])
 PY
 }
-for sh in 4 8; do for t in 48 64 96 128 192; do run EGPU_LUT_SHARE=$sh EGPU_ROWS_PER_THREAD=$t; done; done
+for th in 128 256; do for sh in 2 4; do for t in 24 48 96; do run EGPU_LUT_THREADS=$th EGPU_LUT_SHARE=$sh EGPU_ROWS_PER_THREAD=$t; done; done; done
