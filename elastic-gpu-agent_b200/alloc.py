@@ -26,6 +26,16 @@ def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
 
 
+def _stream(stream):
+    """cudaStream_t for the C ABI.  None -> NULL = the context's own stream.  An integer is a
+    stream handle as torch reports it (`torch.cuda.Stream.cuda_stream`); torch reports the
+    legacy default stream as 0, which the C ABI would read as NULL, so 0 is translated to
+    cudaStreamLegacy (0x1)."""
+    if stream is None:
+        return C.c_void_p(None)
+    return C.c_void_p(1 if int(stream) == 0 else int(stream))
+
+
 class BestFitAllocator:
     """Best-fit device choice over a node-local capacity table on one B200."""
 
@@ -160,24 +170,24 @@ class BestFitAllocator:
 
     # -- snapshot mode, device buffers ---------------------------------------
     def bestfit_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int = 0, d_table_out: int = 0,
-                    commit: bool = False, stream: int = 0, inputs_ready: bool = False):
+                    commit: bool = False, stream: int | None = None, inputs_ready: bool = False):
         flags = (L.F_COMMIT if commit else 0) | (L.F_INPUTS_READY if inputs_ready else 0)
         rc = self._lib.egpu_bestfit_batch_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
                                               C.c_void_p(d_idx), C.c_void_p(d_delta or None),
                                               C.c_void_p(d_table_out or None), flags,
-                                              C.c_void_p(stream or None))
+                                              _stream(stream))
         self._check(rc, "egpu_bestfit_batch_dev")
 
-    def apply_deltas_dev(self, d_deltas: int, G: int, d_table_out: int = 0, commit: bool = True, stream: int = 0):
+    def apply_deltas_dev(self, d_deltas: int, G: int, d_table_out: int = 0, commit: bool = True, stream: int | None = None):
         rc = self._lib.egpu_table_apply_deltas_dev(self._h, C.c_void_p(d_deltas), int(G),
                                                    C.c_void_p(d_table_out or None), 1 if commit else 0,
-                                                   C.c_void_p(stream or None))
+                                                   _stream(stream))
         self._check(rc, "egpu_table_apply_deltas_dev")
 
     def synth_requests_dev(self, dist: int, seed: int, first_row: int, R: int, d_core: int, d_mem: int,
-                           stream: int = 0):
+                           stream: int | None = None):
         rc = self._lib.egpu_synth_requests_dev(self._h, int(dist), int(seed), int(first_row), int(R),
-                                               C.c_void_p(d_core), C.c_void_p(d_mem), C.c_void_p(stream or None))
+                                               C.c_void_p(d_core), C.c_void_p(d_mem), _stream(stream))
         self._check(rc, "egpu_synth_requests_dev")
 
     # -- multi-GPU: peer-memory exchange ----------------------------------------
@@ -195,24 +205,24 @@ class BestFitAllocator:
     def peer_detach(self):
         self._check(self._lib.egpu_peer_detach(self._h), "egpu_peer_detach")
 
-    def bestfit_shard_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, step: int, stream: int = 0,
+    def bestfit_shard_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, step: int, stream: int | None = None,
                           inputs_ready: bool = False):
         rc = self._lib.egpu_bestfit_batch_shard_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
                                                     C.c_void_p(d_idx), C.c_void_p(d_delta or None),
                                                     L.F_INPUTS_READY if inputs_ready else 0, int(step),
-                                                    C.c_void_p(stream or None))
+                                                    _stream(stream))
         self._check(rc, "egpu_bestfit_batch_shard_dev")
 
-    def apply_peers_dev(self, step: int, d_table_out: int = 0, commit: bool = False, stream: int = 0):
+    def apply_peers_dev(self, step: int, d_table_out: int = 0, commit: bool = False, stream: int | None = None):
         rc = self._lib.egpu_table_apply_peers_dev(self._h, int(step), C.c_void_p(d_table_out or None),
-                                                  1 if commit else 0, C.c_void_p(stream or None))
+                                                  1 if commit else 0, _stream(stream))
         self._check(rc, "egpu_table_apply_peers_dev")
 
-    def apply_peers_multi_dev(self, first_step: int, d_table_outs: list[int], commit: bool = False, stream: int = 0):
+    def apply_peers_multi_dev(self, first_step: int, d_table_outs: list[int], commit: bool = False, stream: int | None = None):
         n = len(d_table_outs)
         arr = (C.c_void_p * n)(*[C.c_void_p(p or None) for p in d_table_outs])
         rc = self._lib.egpu_table_apply_peers_multi_dev(self._h, int(first_step), n, arr, 1 if commit else 0,
-                                                        C.c_void_p(stream or None))
+                                                        _stream(stream))
         self._check(rc, "egpu_table_apply_peers_multi_dev")
 
     @property

@@ -237,7 +237,7 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
                                    table_out, flags, slot_step);
 }
 
-template <int DT, int THREADS, int VEC>
+template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
@@ -249,26 +249,23 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     const int warp = tid >> 5;
     const bool late = (flags & kFlagLateWait) != 0;
     if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
-    pdl_trigger();
+    if (flags & kFlagEarlyTrigger) pdl_trigger();
 
     const long long nvec = R >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * THREADS;
     long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
 
-    // issue the first trip's loads before anything else: the request stream is the only HBM
-    // traffic that matters.  VEC 128-bit vectors per array per trip, the next trip's VEC
-    // already in flight while this one is scored: 2 * VEC * 32 bytes per thread on the wire.
-    int4 c[VEC], m[VEC];
-    bool has[VEC];
-#pragma unroll
-    for (int u = 0; u < VEC; ++u) {
-        has[u] = (v + u * stride) < nvec;
-        c[u] = make_int4(0, 0, 0, 0);
-        m[u] = c[u];
-        if (has[u]) {
-            c[u] = ld_stream_v4(req_core + 4 * (v + u * stride));
-            m[u] = ld_stream_v4(req_mem + 4 * (v + u * stride));
-        }
+    // issue the first tile's loads before anything else: the request stream is
+    // the only HBM traffic that matters
+    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
+    bool has0 = v < nvec, has1 = (v + stride) < nvec;
+    if (has0) {
+        c0 = ld_stream_v4(req_core + 4 * v);
+        m0 = ld_stream_v4(req_mem + 4 * v);
+    }
+    if (has1) {
+        c1 = ld_stream_v4(req_core + 4 * (v + stride));
+        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
     }
 
     // sorted table rows: uniform loads straight into registers, no barrier
@@ -301,30 +298,24 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         return r;
     };
 
-    while (has[0]) {
-        const long long vn = v + VEC * stride;
-        int4 nc[VEC], nm[VEC];
-        bool nhas[VEC];
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-            nhas[u] = (vn + u * stride) < nvec;
-            nc[u] = make_int4(0, 0, 0, 0);
-            nm[u] = nc[u];
-            if (nhas[u]) {
-                nc[u] = ld_stream_v4(req_core + 4 * (vn + u * stride));
-                nm[u] = ld_stream_v4(req_mem + 4 * (vn + u * stride));
-            }
+    while (has0) {
+        const long long vn = v + 2 * stride;
+        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
+        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
+        if (nhas0) {
+            nc0 = ld_stream_v4(req_core + 4 * vn);
+            nm0 = ld_stream_v4(req_mem + 4 * vn);
         }
-#pragma unroll
-        for (int u = 0; u < VEC; ++u)
-            if (has[u]) st_stream_v4(out_idx + 4 * (v + u * stride), decide4(c[u], m[u]));
+        if (nhas1) {
+            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
+            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
+        }
+        st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
+        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
         v = vn;
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-            has[u] = nhas[u];
-            c[u] = nc[u];
-            m[u] = nm[u];
-        }
+        has0 = nhas0;
+        has1 = nhas1;
+        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
     // ragged tail: R % 4 rows, scalar
     if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
@@ -350,7 +341,7 @@ bestfit_sorted_packed_kernel(DevState* __restrict__ st, const uint32_t* __restri
     const int warp = tid >> 5;
     const bool late = (flags & kFlagLateWait) != 0;
     if (!late) pdl_wait();
-    pdl_trigger();
+    if (flags & kFlagEarlyTrigger) pdl_trigger();
 
     // A warp takes chunks of 512 requests (2 KiB in, 512 B out): four fully coalesced 128-bit
     // loads per lane (lane-contiguous, 512 B per instruction) and four coalesced 32-bit stores.
@@ -432,8 +423,7 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    pdl_wait();
-    pdl_trigger();
+    pdl_wait();  // never triggers early: the literal variant keeps plain stream semantics
     const int D = st->D;
     hist_zero<DT, THREADS>(s, warp, lane);
     if (tid < D) {
@@ -572,7 +562,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     const int phase = lane / LW;
     const bool late = (flags & kFlagLateWait) != 0;
     if (!late) pdl_wait();
-    pdl_trigger();
+    if (flags & kFlagEarlyTrigger) pdl_trigger();
 
     const long long nvec = R >> 2;
     const long long stride = static_cast<long long>(gridDim.x) * THREADS;
@@ -1074,7 +1064,7 @@ namespace {
 template <int DT, int THREADS>
 SnapLaunch make_launch(bool grid_variant) {
     SnapLaunch l;
-    l.fn = grid_variant ? bestfit_grid_kernel<DT, THREADS> : bestfit_sorted_kernel<DT, THREADS, 2>;
+    l.fn = grid_variant ? bestfit_grid_kernel<DT, THREADS> : bestfit_sorted_kernel<DT, THREADS>;
     l.threads = THREADS;
     l.smem = sizeof(SnapSmem<DT, THREADS>);
     l.ctas_per_sm = 0;
@@ -1118,9 +1108,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
-    // D <= 8 on a pipelined stream: the deeper-prefetch build (4 vectors per array per trip)
-    const bool vec4 = !grid_variant && !lut_variant && bucket == 0 && ctx->vec == 4 && (user_flags & EGPU_F_INPUTS_READY);
-    SnapLaunch& l = ctx->snap[vec4 ? 3 : grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
+    SnapLaunch& l = ctx->snap[grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
     if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
         int per_sm = 0;
         if (lut_variant) {
@@ -1140,7 +1128,6 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
             l = pick_launch(ctx->D, grid_variant);
-            if (vec4) l.fn = bestfit_sorted_kernel<8, 256, 4>;
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
         }
@@ -1179,6 +1166,11 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             if (mine[k].lo < ctx->group_out[i].hi && ctx->group_out[i].lo < mine[k].hi) pipelined = false;
     if (pipelined) flags |= kFlagLateWait;
     else ctx->group_len = 0;
+    // Early trigger (griddepcontrol.launch_dependents before the work is done) only helps when
+    // the next launch is another scan of a pipelined stream, so only those launches do it.
+    // (Checked on B200, scripts/probes/pdl_event_probe.cu and scripts/eager_probe.py: events
+    // and ordinary kernels enqueued after a PDL launch still wait for its completion.)
+    if (user_flags & EGPU_F_INPUTS_READY) flags |= kFlagEarlyTrigger;
     const unsigned long long slot = (finalize ? (ctx->seq % kEpiSlots) : static_cast<unsigned long long>(kEpiSlots)) |
                                     (push_step_plus1 << 8);
 
@@ -1349,7 +1341,6 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
         if (const char* e = std::getenv("EGPU_REPLAY_GENERAL")) ctx->replay_general = std::atoi(e) != 0;
-        if (const char* e = std::getenv("EGPU_VEC")) ctx->vec = std::atoi(e) == 4 ? 4 : 2;
         if (const char* e = std::getenv("EGPU_LUT_THREADS")) ctx->lut_threads = std::atoi(e) == 128 ? 128 : 256;
         if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
             const int v = std::atoi(e);

@@ -28,7 +28,7 @@ struct SnapLaunch {
 
 struct egpu_ctx {
     std::mutex mu;
-    SnapLaunch snap[4][4];            // [sorted, grid, lut, sorted with VEC = 4][D bucket]
+    SnapLaunch snap[3][4];            // [sorted, grid, lut][D bucket]
     DevLut* d_lut = nullptr;
     XchgBuf* d_xchg = nullptr;        // this rank's exchange buffer (exported to the peers over CUDA IPC)
     void* peer_open[kMaxRanks] = {};  // peers' buffers as opened here (nullptr for own rank)
@@ -66,7 +66,6 @@ struct egpu_ctx {
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     int packed_ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the packed-format scan per D bucket, 0 = not asked yet
-    int vec = 2;                      // 128-bit vectors per array per trip for D <= 8 (EGPU_VEC = 2 | 4)
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
     int lut_threads = 256;            // CTA size of the lookup scan (EGPU_LUT_THREADS = 128 | 256)
     int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)

@@ -47,6 +47,9 @@ constexpr int kFlagLateWait = 4;  // programmatic dependent launch: this launch 
                                   // successor at once and waits for its predecessor only
                                   // before it exits (stream order is kept, nothing else)
 
+constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before the scan: only on
+                                      // streams the caller declared pipelined (EGPU_F_INPUTS_READY)
+
 // lane-private demand accumulators pack (core sum << 38 | mem sum) in 64 bits
 constexpr int kAccShift = 38;
 

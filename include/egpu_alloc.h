@@ -86,8 +86,10 @@ extern "C" {
 /* flags of egpu_bestfit_batch_dev */
 #define EGPU_F_COMMIT        1   /* table' replaces the current table */
 #define EGPU_F_INPUTS_READY  2   /* the request arrays were complete before the previous
-                                    launch on this stream: the scan may overlap that
-                                    launch's tail (programmatic dependent launch) */
+                                    launch on this stream: consecutive scans may overlap
+                                    (programmatic dependent launch); anything else
+                                    enqueued later on the stream still sees them
+                                    complete. */
 
 /* kernel variants for the snapshot scan (egpu_set_variant) */
 #define EGPU_VARIANT_AUTO    0   /* SORTED for D <= 16, LUT above */
@@ -156,7 +158,8 @@ void egpu_host_free(egpu_ctx* ctx, void* p);
 /* ---- snapshot mode, device buffers (bench / multi-GPU plumbing) -------- */
 
 /* Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
- * context's own stream).  d_delta is int64[2*D]: core sums then mem sums; it
+ * context's own non-blocking stream — to name the legacy default stream pass
+ * cudaStreamLegacy, not 0).  d_delta is int64[2*D]: core sums then mem sums; it
  * is overwritten, not accumulated.  d_table_out (may be NULL) receives
  * int32[3*D]: free_core', free_mem', oversub.  flags: EGPU_F_*.  The three
  * request/index arrays must be 16-byte aligned (128-bit accesses). */

@@ -362,6 +362,41 @@ def test_pipelined_launches_many_small_batches(alloc, oracle_c, egpu):
     assert np.array_equal(shared.cpu().numpy(), dl[n - 1])
 
 
+def test_events_after_launches_see_completed_scans(alloc, egpu):
+    """Stream semantics: an event recorded after scans (plain or pipelined with
+    inputs_ready=True, which trigger their successors early) must not complete before the
+    indices are written — checked from another stream that waits only for the event."""
+    import torch
+    w = egpu.synth.workload("cfg3")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    R = 32 << 20
+    st = torch.cuda.Stream()
+    side = torch.cuda.Stream()
+    sh = st.cuda_stream
+    with torch.cuda.stream(st):
+        c = torch.empty(R, dtype=torch.int32, device="cuda")
+        m = torch.empty_like(c)
+        alloc.synth_requests_dev(3, 7, 0, R, c.data_ptr(), m.data_ptr(), sh)
+        outs = [torch.empty(R, dtype=torch.int32, device="cuda") for _ in range(3)]
+        dls = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(3)]
+    torch.cuda.synchronize()
+    for ready in (False, True):
+        with torch.cuda.stream(st):
+            for o in outs:
+                o.fill_(-9)
+        torch.cuda.synchronize()
+        ev = torch.cuda.Event()
+        for i in range(6):
+            alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, outs[i % 3].data_ptr(), dls[i % 3].data_ptr(), 0, False, sh,
+                              inputs_ready=ready)
+        ev.record(st)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            unwritten = (outs[2] == -9).sum() + (outs[0] == -9).sum() + (outs[1] == -9).sum()
+        torch.cuda.synchronize()
+        assert int(unwritten) == 0, (ready, int(unwritten))
+
+
 def test_full_size_properties_64mi(alloc, egpu):
     """BASELINE full size and beyond, checked through size-independent properties:
     forced-infeasible rows are -1, every chosen device is feasible, the demand
