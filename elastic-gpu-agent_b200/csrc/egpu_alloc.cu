@@ -20,1037 +20,8 @@
 
 #include "../../include/egpu_alloc.h"
 
-namespace egpu {
-
-// =============================================================================
-// Snapshot scan
-// =============================================================================
-//
-// Why "sorted" is the fast formulation.  For a fixed table the best-fit device
-// of request (c, m) minimises (fc-c, fm-m, d) over feasible d, which is the same
-// as minimising (fc, fm, d): the request cancels out of the comparison.  So the
-// answer is the FIRST feasible device in the table sorted by (fc, fm, d).  Each
-// CTA sorts the <= 64 table rows once (rank sort in shared memory), every thread
-// keeps the packed sorted rows in registers, and per (request, device) pair the
-// work is: one subtract (both feasibility tests at once, see kGuards), one LOP3
-// producing "sorted position, or a value >= 2^18 if infeasible", and half a
-// 3-input unsigned min (VIMNMX3).  The chosen position maps back to the device
-// index through a shared-memory tile.
-
-template <int DT, int THREADS>
-struct SnapSmem {
-    int32_t sFc[kMaxD];                           // table tile (grid variant; re-sort scratch)
-    int32_t sFm[kMaxD];
-    int32_t sPosDev[kMaxD];
-    unsigned long long sWarpAcc[THREADS / 32][2 * DT];
-    int sLast;
-    int32_t sDevTile[THREADS / 32][DT + 8];           // warp-private: sorted position -> device, [DT] = -1
-    unsigned long long hist[THREADS / 32][DT + 1][32];  // lane-private demand sums; row 0 = "no device"
-};
-
-// Re-derive the sorted view of the table (DevState::sorted_k / sorted_dev /
-// dev_packed).  Called by every thread of ONE CTA after thread d < D has put the
-// new row d into sFc[d] / sFm[d].  Rank sort: position = rows ordering before.
-__device__ __forceinline__ void resort_table_cta(DevState* st, int D, int32_t* sFc, int32_t* sFm,
-                                                 int32_t* sPosDev, int tid) {
-    const int nt = blockDim.x;
-    __syncthreads();
-    for (int d = tid; d < kMaxD; d += nt) sPosDev[d] = -1;
-    __syncthreads();
-    for (int d = tid; d < kMaxD; d += nt) {
-        if (d < D) {
-            const int32_t fc = sFc[d], fm = sFm[d];
-            const uint32_t mine = (static_cast<uint32_t>(fc) << 24) | (static_cast<uint32_t>(fm) << 6) | d;
-            int pos = 0;
-            for (int k = 0; k < D; ++k) {
-                const uint32_t other = (static_cast<uint32_t>(sFc[k]) << 24) | (static_cast<uint32_t>(sFm[k]) << 6) | k;
-                pos += other < mine;
-            }
-            st->sorted_k[pos] = pack_table_word(fc, fm) | (static_cast<uint32_t>(pos) & 31u);
-            st->sorted_dev[pos] = d;
-            sPosDev[pos] = d;
-        } else {  // positions >= D are never produced by a rank
-            st->sorted_k[d] = kPadWord;
-            st->sorted_dev[d] = -1;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long packed = 0;
-        for (int j = 0; j < 8; ++j)
-            packed |= static_cast<unsigned long long>(static_cast<uint32_t>(sPosDev[j]) & 0xffu) << (8 * j);
-        st->dev_packed = packed;
-    }
-}
-
-// First feasible sorted position; >= DT when there is none.
-// Per (request, row) pair: one subtract (IMAD.IADD or IADD3, ptxas balances the FMA and
-// ALU pipes), one 3-input LOP3 ((t ^ G) & M, both masks in registers), half a VIMNMX3.
-template <int N>
-__device__ __forceinline__ uint32_t first_feasible32(const uint32_t* K, uint32_t q, uint32_t gx, uint32_t gm) {
-    uint32_t best = kNoCand;
-#pragma unroll
-    for (int j = 0; j < N; j += 2) {
-        const uint32_t c0 = ((K[j] - q) ^ gx) & gm;
-        const uint32_t c1 = ((K[j + 1] - q) ^ gx) & gm;
-        best = __vimin3_u32(best, c0, c1);
-    }
-    return best;  // 0..N-1, or >= 32
-}
-template <int DT>
-__device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q, uint32_t gx, uint32_t gm) {
-    if constexpr (DT <= 32) {
-        return min(first_feasible32<DT>(K, q, gx, gm), static_cast<uint32_t>(DT));
-    } else {  // positions are stored mod 32: two halves
-        const uint32_t lo = first_feasible32<32>(K, q, gx, gm);
-        const uint32_t hi = first_feasible32<DT - 32>(K + 32, q, gx, gm);
-        return lo < 32u ? lo : (hi < 32u ? 32u + hi : static_cast<uint32_t>(DT));
-    }
-}
-
-template <int DT, int THREADS>
-__device__ __forceinline__ void hist_zero(SnapSmem<DT, THREADS>& s, int warp, int lane) {
-    // lane-private: each lane clears exactly the words it will use -> no barrier
-#pragma unroll
-    for (int d = 0; d <= DT; ++d) s.hist[warp][d][lane] = 0ull;
-}
-
-template <int DT, int THREADS>
-__device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int lane, int32_t idx,
-                                         int32_t core, int32_t mem) {
-    // unconditional: infeasible rows (idx = -1) land in the dummy row 0, whose
-    // content is never read (it may hold garbage from out-of-domain requests)
-    s.hist[warp][idx + 1][lane] +=
-        (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-        static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-}
-
-// Second half of every snapshot epilogue.  `wacc` holds per-warp demand sums in shared
-// memory: core sum of device d of warp w at wacc[w * wstride + core_off + d], mem sum at
-// [... + mem_off + d].  Called by all threads after a __syncthreads().  Publishes the CTA's
-// sums with one red.global.add.u64 per device, takes an arrival ticket, and the last CTA
-// writes delta / table', optionally commits (and re-sorts) the table and resets the slot.
-template <int WARPS>
-__device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
-                                                 int32_t* sFc, int32_t* sFm, int32_t* sPosDev, int* sLast,
-                                                 DevState* st, int D, long long* __restrict__ delta_out,
-                                                 int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
-    // slot_step: bits 0..7 = epilogue slot of this launch; bits 8.. = step + 1 when the demand
-    // vector must also be pushed to the peers' exchange buffers (0 = single GPU)
-    DevState::EpiSlot& ep = st->epi[slot_step & 0xffu];
-    const unsigned long long push = slot_step >> 8;
-    const int tid = threadIdx.x;
-    if (tid < 2 * D) {
-        const int j = tid < D ? core_off + tid : mem_off + (tid - D);
-        unsigned long long tot = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) tot += wacc[w * wstride + j];
-        if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
-        __threadfence();  // only the threads that published sums need to order them before the ticket
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&ep.ticket, 1u);
-        *sLast = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!*sLast) return;
-    __threadfence();
-    const bool fin = (flags & kFlagFinalize) != 0;
-    const bool commit = fin && (flags & kFlagCommit);
-    if (fin && tid < D) {
-        volatile unsigned long long* acc = ep.acc;
-        const long long dc = static_cast<long long>(acc[tid]);
-        const long long dm = static_cast<long long>(acc[kMaxD + tid]);
-        acc[tid] = 0ull;
-        acc[kMaxD + tid] = 0ull;
-        const long long nc = static_cast<long long>(st->free_core[tid]) - dc;
-        const long long nm = static_cast<long long>(st->free_mem[tid]) - dm;
-        const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
-        if (delta_out) {
-            delta_out[tid] = dc;
-            delta_out[D + tid] = dm;
-        }
-        if (push) {  // fused exchange: this rank's vector straight into every rank's buffer
-            const int world = st->peer.world, me = st->peer.rank;
-            const int xs = static_cast<int>((push - 1) % kXchgSlots);
-            for (int p = 0; p < world; ++p) {
-                XchgRow& row = st->peer.buf[p]->slot[xs][me];
-                row.delta[tid] = dc;
-                row.delta[D + tid] = dm;
-            }
-            __threadfence_system();
-        }
-        if (table_out) {
-            table_out[tid] = sat_i32(nc);
-            table_out[D + tid] = sat_i32(nm);
-            table_out[2 * D + tid] = over;
-        }
-        if (commit) {
-            // the committed table stays inside the spec's domain: negative
-            // leftovers clamp to 0 and the oversubscription flag is sticky
-            const int32_t cc = nc < 0 ? 0 : static_cast<int32_t>(nc);
-            const int32_t cm = nm < 0 ? 0 : static_cast<int32_t>(nm);
-            st->free_core[tid] = cc;
-            st->free_mem[tid] = cm;
-            st->oversub[tid] |= over;
-            sFc[tid] = cc;
-            sFm[tid] = cm;
-        }
-    }
-    if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
-    if (push) {
-        __syncthreads();  // every delta store above is fenced; now raise the flags
-        const int world = st->peer.world, me = st->peer.rank;
-        if (tid < world) {
-            unsigned long long* f = &st->peer.buf[tid]->slot[(push - 1) % kXchgSlots][me].flag;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(push) : "memory");
-        }
-    }
-    if (tid == 0) ep.ticket = 0u;
-}
-
-// Demand sums -> global running sums -> (last CTA) delta / table' publication.
-template <int DT, int THREADS>
-__device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
-                                                  long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    __syncwarp();
-    for (int d = 0; d < D; ++d) {
-        const unsigned long long v = s.hist[warp][d + 1][lane];
-        const uint32_t c = static_cast<uint32_t>(v >> kAccShift);
-        const uint32_t ml = static_cast<uint32_t>(v) & 0x7FFFFu;
-        const uint32_t mh = static_cast<uint32_t>(v >> 19) & 0x7FFFFu;
-        const uint32_t sc = __reduce_add_sync(0xffffffffu, c);
-        const uint32_t sl = __reduce_add_sync(0xffffffffu, ml);
-        const uint32_t sh = __reduce_add_sync(0xffffffffu, mh);
-        if (lane == 0) {
-            s.sWarpAcc[warp][d] = sc;
-            s.sWarpAcc[warp][DT + d] = static_cast<unsigned long long>(sl) + (static_cast<unsigned long long>(sh) << 19);
-        }
-    }
-    __syncthreads();
-    epilogue_publish<THREADS / 32>(&s.sWarpAcc[0][0], 2 * DT, 0, DT, s.sFc, s.sFm, s.sPosDev, &s.sLast, st, D, delta_out,
-                                   table_out, flags, slot_step);
-}
-
-template <int DT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
-                      const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const bool late = (flags & kFlagLateWait) != 0;
-    if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
-    if (flags & kFlagEarlyTrigger) pdl_trigger();
-
-    const long long nvec = R >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
-    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
-
-    // issue the first tile's loads before anything else: the request stream is
-    // the only HBM traffic that matters
-    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
-    bool has0 = v < nvec, has1 = (v + stride) < nvec;
-    if (has0) {
-        c0 = ld_stream_v4(req_core + 4 * v);
-        m0 = ld_stream_v4(req_mem + 4 * v);
-    }
-    if (has1) {
-        c1 = ld_stream_v4(req_core + 4 * (v + stride));
-        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
-    }
-
-    // sorted table rows: uniform loads straight into registers, no barrier
-    const int D = st->D;
-    uint32_t K[DT];
-#pragma unroll
-    for (int j = 0; j < DT; j += 4) {
-        const uint4 k4 = *reinterpret_cast<const uint4*>(&st->sorted_k[j]);
-        K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
-    }
-    const uint32_t gx = st->cand_xor, gm = st->cand_mask;
-    // warp-private tile of the position -> device map: only a warp-level barrier
-    int32_t* tile = s.sDevTile[warp];
-    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
-    hist_zero<DT, THREADS>(s, warp, lane);
-    __syncwarp();
-
-    auto decide = [&](int32_t core, int32_t mem) -> int32_t {
-        const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem), gx, gm);
-        const int32_t idx = tile[best];  // best <= DT; tile[DT] = -1
-        hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
-        return idx;
-    };
-    auto decide4 = [&](const int4& c, const int4& m) -> int4 {
-        int4 r;
-        r.x = decide(c.x, m.x);
-        r.y = decide(c.y, m.y);
-        r.z = decide(c.z, m.z);
-        r.w = decide(c.w, m.w);
-        return r;
-    };
-
-    while (has0) {
-        const long long vn = v + 2 * stride;
-        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
-        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
-        if (nhas0) {
-            nc0 = ld_stream_v4(req_core + 4 * vn);
-            nm0 = ld_stream_v4(req_mem + 4 * vn);
-        }
-        if (nhas1) {
-            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
-            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
-        }
-        st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
-        v = vn;
-        has0 = nhas0;
-        has1 = nhas1;
-        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
-    }
-    // ragged tail: R % 4 rows, scalar
-    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
-        const long long r = (nvec << 2) + tid;
-        out_idx[r] = decide(req_core[r], req_mem[r]);
-    }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
-    if (late) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
-}
-
-// Packed wire format (include/egpu_alloc.h: egpu_bestfit_batch_packed): one uint32 per request
-// (core << 18 | mem, anything >= 2^25 = "no valid request") and one int8 per decision - 5 bytes
-// per decision instead of 12.  Same scan, same epilogue.
-template <int DT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-bestfit_sorted_packed_kernel(DevState* __restrict__ st, const uint32_t* __restrict__ req, long long R,
-                             signed char* __restrict__ out_idx8, long long* __restrict__ delta_out,
-                             int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const bool late = (flags & kFlagLateWait) != 0;
-    if (!late) pdl_wait();
-    if (flags & kFlagEarlyTrigger) pdl_trigger();
-
-    // A warp takes chunks of 512 requests (2 KiB in, 512 B out): four fully coalesced 128-bit
-    // loads per lane (lane-contiguous, 512 B per instruction) and four coalesced 32-bit stores.
-    const long long nchunk = R >> 9;
-    const long long wstride = static_cast<long long>(gridDim.x) * (THREADS / 32);
-    long long ch = static_cast<long long>(blockIdx.x) * (THREADS / 32) + warp;
-    uint4 p[4];
-    bool has = ch < nchunk;
-    auto load_chunk = [&](long long ci, uint4 (&dst)[4]) {
-        const uint4* src = reinterpret_cast<const uint4*>(req) + 128 * ci + lane;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int4 t = ld_stream_v4(reinterpret_cast<const int32_t*>(src + 32 * u));
-            dst[u] = make_uint4(t.x, t.y, t.z, t.w);
-        }
-    };
-    if (has) load_chunk(ch, p);
-
-    const int D = st->D;
-    uint32_t K[DT];
-#pragma unroll
-    for (int j = 0; j < DT; j += 4) {
-        const uint4 k4 = *reinterpret_cast<const uint4*>(&st->sorted_k[j]);
-        K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
-    }
-    const uint32_t gx = st->cand_xor, gm = st->cand_mask;
-    int32_t* tile = s.sDevTile[warp];
-    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
-    hist_zero<DT, THREADS>(s, warp, lane);
-    __syncwarp();
-
-    auto decide = [&](uint32_t pw) -> uint32_t {
-        // core << 18 | mem  ->  core << 24 | mem << 5; out-of-format words fail every guard
-        const uint32_t q = (pw >> 25) ? (127u << 24) : (((pw & ~0x3FFFFu) << 6) | ((pw & 0x3FFFFu) << 5));
-        const uint32_t best = first_feasible<DT>(K, q, gx, gm);
-        const int32_t idx = tile[best];
-        hist_add<DT, THREADS>(s, warp, lane, idx, static_cast<int32_t>((pw >> 18) & 127u), static_cast<int32_t>(pw & 0x3FFFFu));
-        return static_cast<uint32_t>(idx) & 0xffu;
-    };
-    auto decide4 = [&](const uint4& v) -> uint32_t {
-        return decide(v.x) | (decide(v.y) << 8) | (decide(v.z) << 16) | (decide(v.w) << 24);
-    };
-    while (has) {
-        const long long cn = ch + wstride;
-        const bool nhas = cn < nchunk;
-        uint4 np[4];
-        if (nhas) load_chunk(cn, np);
-        uint32_t* out32 = reinterpret_cast<uint32_t*>(out_idx8) + 128 * ch + lane;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t r4 = decide4(p[u]);
-            asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(out32 + 32 * u), "r"(r4) : "memory");
-        }
-        ch = cn;
-        has = nhas;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) p[u] = np[u];
-    }
-    // ragged tail: R % 512 rows, scalar, spread over the first CTA
-    if (blockIdx.x == 0) {
-        for (long long r = (nchunk << 9) + tid; r < R; r += THREADS) out_idx8[r] = static_cast<signed char>(decide(req[r]));
-    }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
-    if (late) pdl_wait();
-}
-
-// The north-star's literal formulation: every (device, request) pair is scored
-// with the spec's packed key (lc << 24 | lm << 6 | d) against a shared-memory
-// tile of the table and the row is reduced with a running min.  Kept as an
-// independent second device implementation (tests compare the two) and as the
-// baseline the sorted variant is measured against.
-template <int DT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
-                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    pdl_wait();  // never triggers early: the literal variant keeps plain stream semantics
-    const int D = st->D;
-    hist_zero<DT, THREADS>(s, warp, lane);
-    if (tid < D) {
-        s.sFc[tid] = st->free_core[tid];
-        s.sFm[tid] = st->free_mem[tid];
-    }
-    __syncthreads();
-
-    auto decide = [&](int32_t core, int32_t mem) -> int32_t {
-        int32_t best = 0x7fffffff;
-        const bool valid = (core | mem) >= 0;
-        for (int d = 0; d < D; ++d) {
-            const int32_t lc = s.sFc[d] - core;
-            const int32_t lm = s.sFm[d] - mem;
-            const int32_t key = (lc << 24) | (lm << 6) | d;
-            best = (valid && (lc | lm) >= 0) ? min(best, key) : best;
-        }
-        const int32_t idx = best == 0x7fffffff ? -1 : (best & 63);
-        hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
-        return idx;
-    };
-
-    const long long nvec = R >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
-    for (long long v = static_cast<long long>(blockIdx.x) * THREADS + tid; v < nvec; v += stride) {
-        const int4 c = ld_stream_v4(req_core + 4 * v);
-        const int4 m = ld_stream_v4(req_mem + 4 * v);
-        int4 r;
-        r.x = decide(c.x, m.x);
-        r.y = decide(c.y, m.y);
-        r.z = decide(c.z, m.z);
-        r.w = decide(c.w, m.w);
-        st_stream_v4(out_idx + 4 * v, r);
-    }
-    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
-        const long long r = (nvec << 2) + tid;
-        out_idx[r] = decide(req_core[r], req_mem[r]);
-    }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
-}
-
-// =============================================================================
-// Lookup-table scan for large D (EGPU_VARIANT_LUT; AUTO picks it for D > 16)
-// =============================================================================
-//
-// The register-resident scan above costs 3.5 instructions per (request, device) pair:
-// fine for D = 8 (HBM-bound), ALU-bound by 4x at D = 64.  The lookup form needs three
-// shared-memory reads and ~20 instructions per request whatever D is.
-
-// Builds DevLut from the sorted view in DevState.  One CTA; runs after every table change.
-__global__ void __launch_bounds__(256)
-lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
-    __shared__ uint32_t sFm[kMaxD], sFcs[kMaxD], sV[kMaxD];
-    __shared__ int sFirst[kMaxD], sRidx[kMaxD], sNv;
-    const int tid = threadIdx.x;
-    const int D = st->D;
-    if (tid < kMaxD) {
-        const uint32_t k = tid < D ? st->sorted_k[tid] : 0u;
-        sFm[tid] = (k >> 5) & 0x3FFFFu;
-        sFcs[tid] = (k >> 24) & 0x7Fu;
-        sV[tid] = 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    if (tid < D) {  // first occurrence of its fm value?
-        int first = 1;
-        for (int k = 0; k < tid; ++k) first &= (sFm[k] != sFm[tid]);
-        sFirst[tid] = first;
-    }
-    __syncthreads();
-    if (tid < D) {  // ridx = number of distinct values below mine
-        int r = 0;
-        for (int k = 0; k < D; ++k) r += (sFirst[k] && sFm[k] < sFm[tid]);
-        sRidx[tid] = r;
-        sV[r] = sFm[tid];
-    }
-    if (tid == 0) {
-        int nv = 0;
-        for (int k = 0; k < D; ++k) nv += sFirst[k];
-        sNv = nv;
-        lut->nv = nv;
-    }
-    __syncthreads();
-    const int nv = sNv;
-    if (tid < kMaxD) lut->v[tid] = sV[tid];
-    if (tid < 128) {  // start[c] = first sorted position with fc >= c
-        int n = 0;
-        for (int k = 0; k < D; ++k) n += (sFcs[k] < static_cast<uint32_t>(tid));
-        lut->start[tid] = static_cast<uint8_t>(n);
-    }
-    if (tid < kLutStride) {  // column r of a[][]: walk the suffixes from the back
-        const int r = tid;
-        uint8_t cur = 0xFF;
-        for (int srow = kMaxD; srow >= 0; --srow) {
-            if (srow < D && sRidx[srow] >= r) cur = static_cast<uint8_t>(st->sorted_dev[srow]);
-            if (srow > D) cur = 0xFF;
-            lut->a[srow * kLutStride + r] = cur;
-        }
-    }
-    for (int b = tid; b < kLutBuckets; b += blockDim.x) {
-        const uint32_t lo_v = static_cast<uint32_t>(b) << 6, hi_v = lo_v + 64u;
-        int lo = 0, hi = 0;
-        for (int k = 0; k < nv; ++k) {
-            lo += (sV[k] < lo_v);
-            hi += (sV[k] < hi_v);
-        }
-        lut->bucket[b] = static_cast<uint16_t>(lo | ((hi - lo) << 8));
-    }
-}
-
-// Demand sums of the lookup scan: lane-private like SnapSmem::hist, but SHARE lanes share
-// one accumulator (SHARE = 1, 2 or 4) and take turns, SHARE phases per update.  D = 64
-// with SHARE = 1 costs 16.6 KB per warp, which caps an SM at 8-12 warps; sharing trades
-// a few issue slots (the scan is nowhere near ALU-bound) for occupancy.
-template <int THREADS, int SHARE>
-struct LutSmem {
-    DevLut lut;
-    unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
-    int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    int sLast;
-    alignas(16) unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];  // zeroed with 128-bit stores
-};
-
-template <int THREADS, int SHARE>
-__global__ void __launch_bounds__(THREADS)
-bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
-                   const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
-                   const DevLut* __restrict__ glut) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& sm = *reinterpret_cast<LutSmem<THREADS, SHARE>*>(smem_raw);
-    constexpr int LW = 32 / SHARE;  // accumulator columns per warp
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int col = lane & (LW - 1);
-    const int phase = lane / LW;
-    const bool late = (flags & kFlagLateWait) != 0;
-    if (!late) pdl_wait();
-    if (flags & kFlagEarlyTrigger) pdl_trigger();
-
-    const long long nvec = R >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
-    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
-    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
-    bool has0 = v < nvec, has1 = (v + stride) < nvec;
-    if (has0) {
-        c0 = ld_stream_v4(req_core + 4 * v);
-        m0 = ld_stream_v4(req_mem + 4 * v);
-    }
-    if (has1) {
-        c1 = ld_stream_v4(req_core + 4 * (v + stride));
-        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
-    }
-    // shared-memory tile of the lookup tables (12.8 KB, L2-resident source)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(glut);
-        uint4* dst = reinterpret_cast<uint4*>(&sm.lut);
-        for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
-    }
-    const int D = st->D;
-    {   // zero this warp's accumulators with 128-bit stores
-        uint4* hz = reinterpret_cast<uint4*>(&sm.hist[warp][0][0]);
-        constexpr int n16 = (kMaxD + 1) * LW * 8 / 16;
-        for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncthreads();
-    const DevLut& L = sm.lut;
-
-    // lookups for one request: no data-dependent loop on the common path
-    auto lookup = [&](int32_t core, int32_t mem) -> int32_t {
-        const uint32_t c = min(static_cast<uint32_t>(core), 127u);
-        const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
-        const uint32_t srow = L.start[c];
-        const uint32_t e = L.bucket[m >> 6];
-        const uint32_t lo = e & 0xffu, n = e >> 8;
-        uint32_t rank = lo + ((n != 0u) & (L.v[lo & 63u] < m));
-        for (uint32_t i = 1; i < n; ++i) rank += (L.v[lo + i] < m);  // rare: several distinct fm in one 64 MiB bucket
-        return static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
-    };
-    // Demand sums for the four requests of one vector at once.  Requests of this thread that
-    // chose the same device are merged first (the later one is redirected to the dummy row
-    // with nothing to add), so the four read-modify-writes are independent and can be issued
-    // as four loads, four adds, four stores per phase instead of four dependent chains.
-    auto accumulate4 = [&](const int4& r, const int4& c, const int4& m) {
-        auto val = [](int32_t core, int32_t mem) {
-            return (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-                   static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-        };
-        int32_t i0 = r.x, i1 = r.y, i2 = r.z, i3 = r.w;
-        unsigned long long v0 = val(c.x, m.x), v1 = val(c.y, m.y), v2 = val(c.z, m.z), v3 = val(c.w, m.w);
-        if (i0 < 0) v0 = 0;  // infeasible rows carry out-of-domain values: keep the dummy row harmless
-        if (i1 < 0) v1 = 0;
-        if (i2 < 0) v2 = 0;
-        if (i3 < 0) v3 = 0;
-        if (i3 == i2) { v2 += v3; v3 = 0; i3 = -1; }
-        if (i3 == i1) { v1 += v3; v3 = 0; i3 = -1; }
-        if (i3 == i0) { v0 += v3; v3 = 0; i3 = -1; }
-        if (i2 == i1) { v1 += v2; v2 = 0; i2 = -1; }
-        if (i2 == i0) { v0 += v2; v2 = 0; i2 = -1; }
-        if (i1 == i0) { v0 += v1; v1 = 0; i1 = -1; }
-        unsigned long long* h0 = &sm.hist[warp][i0 + 1][col];
-        unsigned long long* h1 = &sm.hist[warp][i1 + 1][col];
-        unsigned long long* h2 = &sm.hist[warp][i2 + 1][col];
-        unsigned long long* h3 = &sm.hist[warp][i3 + 1][col];
-#pragma unroll
-        for (int p = 0; p < SHARE; ++p) {
-            if (SHARE == 1 || phase == p) {
-                const unsigned long long a0 = *h0, a1 = *h1, a2 = *h2, a3 = *h3;
-                *h0 = a0 + v0;
-                *h1 = a1 + v1;
-                *h2 = a2 + v2;
-                *h3 = a3 + v3;  // several redirected requests may all hit the dummy row: its content is never read
-            }
-            if (SHARE > 1) __syncwarp();
-        }
-    };
-    auto decide4 = [&](const int4& c, const int4& m) -> int4 {
-        int4 r;
-        r.x = lookup(c.x, m.x);
-        r.y = lookup(c.y, m.y);
-        r.z = lookup(c.z, m.z);
-        r.w = lookup(c.w, m.w);
-        accumulate4(r, c, m);
-        return r;
-    };
-    while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: accumulate() synchronises the warp
-        const long long vn = v + 2 * stride;
-        const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
-        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
-        if (nhas0) {
-            nc0 = ld_stream_v4(req_core + 4 * vn);
-            nm0 = ld_stream_v4(req_mem + 4 * vn);
-        }
-        if (nhas1) {
-            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
-            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
-        }
-        // lanes past the end carry core = mem = -1: infeasible, lands in the dummy row
-        if (!has0) { c0 = make_int4(-1, -1, -1, -1); m0 = c0; }
-        if (!has1) { c1 = make_int4(-1, -1, -1, -1); m1 = c1; }
-        const int4 r0 = decide4(c0, m0);
-        const int4 r1 = decide4(c1, m1);
-        if (has0) st_stream_v4(out_idx + 4 * v, r0);
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), r1);
-        v = vn;
-        has0 = nhas0;
-        has1 = nhas1;
-        c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
-    }
-    if (blockIdx.x == 0 && warp == 0) {  // ragged tail: R % 4 rows; whole warp takes part in accumulate()
-        const bool mine = lane < static_cast<int>(R & 3);
-        const long long r = (nvec << 2) + lane;
-        const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
-        const int32_t idx = lookup(c, m);
-        accumulate4(make_int4(idx, -1, -1, -1), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0));
-        if (mine) out_idx[r] = idx;
-    }
-    // warp sums -> sWarpAcc, transposed: lane L adds up the LW columns of devices L and L + 32
-    // (rotated start column: conflict-free), instead of three warp reductions per device
-    __syncwarp();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int d = lane + 32 * half;
-        unsigned long long sc = 0, smem_sum = 0;
-        if (d < D) {
-#pragma unroll 4
-            for (int k = 0; k < LW; ++k) {
-                const unsigned long long hv = sm.hist[warp][d + 1][(k + lane) & (LW - 1)];
-                sc += hv >> kAccShift;
-                smem_sum += hv & ((1ull << kAccShift) - 1ull);
-            }
-        }
-        sm.sWarpAcc[warp][d] = sc;
-        sm.sWarpAcc[warp][kMaxD + d] = smem_sum;
-    }
-    __syncthreads();
-    epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
-                                   delta_out, table_out, flags, slot_step);
-    if (late) pdl_wait();
-}
-
-// Multi-GPU step 2: table' = table - sum over ranks of their demand vectors.
-__global__ void __launch_bounds__(kMaxD)
-apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ deltas,
-                    int G, int32_t* __restrict__ table_out, int commit) {
-    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    const int D = st->D;
-    const int d = threadIdx.x;
-    if (d < D) {
-        long long dc = 0, dm = 0;
-        for (int g = 0; g < G; ++g) {
-            dc += deltas[static_cast<long long>(g) * 2 * D + d];
-            dm += deltas[static_cast<long long>(g) * 2 * D + D + d];
-        }
-        const long long nc = static_cast<long long>(st->free_core[d]) - dc;
-        const long long nm = static_cast<long long>(st->free_mem[d]) - dm;
-        const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
-        if (table_out) {
-            table_out[d] = sat_i32(nc);
-            table_out[D + d] = sat_i32(nm);
-            table_out[2 * D + d] = over;
-        }
-        if (commit) {
-            const int32_t cc = nc < 0 ? 0 : static_cast<int32_t>(nc);
-            const int32_t cm = nm < 0 ? 0 : static_cast<int32_t>(nm);
-            st->free_core[d] = cc;
-            st->free_mem[d] = cm;
-            st->oversub[d] |= over;
-            sFc[d] = cc;
-            sFm[d] = cm;
-        }
-    }
-    if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, d);
-}
-
-// Multi-GPU step 2, peer-memory form: wait until every rank's demand vector of `step` has
-// landed in THIS rank's exchange buffer, then apply their sum.  One CTA.  The spin gives up
-// after ~2 s (a rank died): DevState::peer_timeout records it and the table is left alone.
-struct ApplyOuts {
-    int32_t* table_out[8];
-};
-
-__global__ void __launch_bounds__(kMaxD)
-apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus1, int nsteps, ApplyOuts outs, int commit) {
-    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    __shared__ int sOk;
-    const int D = st->D;
-    const int d = threadIdx.x;
-    const int world = st->peer.world, me = st->peer.rank;
-    // running table across the steps of this launch (only installed when commit is set)
-    long long cur_c = d < D ? st->free_core[d] : 0, cur_m = d < D ? st->free_mem[d] : 0;
-    int32_t sticky = 0;
-    for (int k = 0; k < nsteps; ++k) {
-        const unsigned long long step_plus1 = first_step_plus1 + k;
-        XchgRow* rows = st->peer.buf[me]->slot[(step_plus1 - 1) % kXchgSlots];
-        if (d == 0) sOk = 1;
-        __syncthreads();
-        if (d < world) {
-            unsigned long long f = 0;
-            const long long t0 = clock64();
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[d].flag) : "memory");
-                if (f == step_plus1) break;
-                if (clock64() - t0 > 4000000000ll) {
-                    sOk = 0;
-                    break;
-                }
-                __nanosleep(100);
-            }
-        }
-        __syncthreads();
-        if (!sOk) {
-            if (d == 0) st->peer_timeout = step_plus1;
-            return;
-        }
-        long long dc = 0, dm = 0;
-        if (d < D) {
-            for (int g = 0; g < world; ++g) {
-                dc += rows[g].delta[d];
-                dm += rows[g].delta[D + d];
-            }
-        }
-        __syncthreads();
-        // consume the flags: a replayed CUDA graph pushes the same step numbers again, and a
-        // stale flag must not look like the new one.  (The slot is not written again before
-        // this rank has applied 16 more steps, see the header.)
-        if (d < world) rows[d].flag = 0ull;
-        if (d < D) {
-            const long long nc = cur_c - dc, nm = cur_m - dm;
-            const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
-            if (outs.table_out[k]) {
-                outs.table_out[k][d] = sat_i32(nc);
-                outs.table_out[k][D + d] = sat_i32(nm);
-                outs.table_out[k][2 * D + d] = over;
-            }
-            if (commit) {  // the next step of this launch is applied on top of this one
-                cur_c = nc < 0 ? 0 : nc;
-                cur_m = nm < 0 ? 0 : nm;
-                sticky |= over;
-            }
-        }
-    }
-    if (commit) {
-        if (d < D) {
-            st->free_core[d] = static_cast<int32_t>(cur_c);
-            st->free_mem[d] = static_cast<int32_t>(cur_m);
-            st->oversub[d] |= sticky;
-            sFc[d] = static_cast<int32_t>(cur_c);
-            sFm[d] = static_cast<int32_t>(cur_m);
-        }
-        resort_table_cta(st, D, sFc, sFm, sPosDev, d);
-    }
-}
-
-// =============================================================================
-// Synthetic request generator (same counter RNG as synth.py)
-// =============================================================================
-__device__ __forceinline__ unsigned long long mix64(unsigned long long seed, unsigned long long stream,
-                                                    unsigned long long i) {
-    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull + i;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ int32_t uniform_i32(unsigned long long seed, unsigned long long stream,
-                                               unsigned long long i, int lo, int hi) {
-    const unsigned long long z = mix64(seed, stream, i);
-    const unsigned long long n = static_cast<unsigned long long>(hi - lo + 1);
-    return lo + static_cast<int32_t>(((z >> 32) * n) >> 32);
-}
-
-__global__ void synth_requests_kernel(int dist, unsigned long long seed, long long first_row, long long R,
-                                      int32_t* __restrict__ req_core, int32_t* __restrict__ req_mem) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < R; k += stride) {
-        const unsigned long long r = static_cast<unsigned long long>(first_row + k);
-        int32_t core, mem;
-        if (dist == 2) {
-            const int ci = uniform_i32(seed, 2, r, 0, 5);
-            const int mi = uniform_i32(seed, 3, r, 0, 6);
-            core = ci == 0 ? 5 : ci == 1 ? 10 : ci == 2 ? 20 : ci == 3 ? 25 : ci == 4 ? 50 : 100;
-            mem = 256 << mi;
-        } else {
-            core = uniform_i32(seed, 2, r, 1, 100);
-            mem = uniform_i32(seed, 3, r, 1, dist == 3 ? 65536 : 24576);
-            if ((r & 15ull) == 15ull) {
-                if (((r >> 4) & 1ull) == 0ull) core = 101;
-                else mem = 183359 + 1;
-            }
-        }
-        req_core[k] = core;
-        req_mem[k] = mem;
-    }
-}
-
-// =============================================================================
-// Sequential mode: one warp.  D <= 8: table in registers (replay8_kernel, below the general
-// one); otherwise lane = device (two per lane when D > 32)
-// =============================================================================
-//
-// Request k sees the table after k-1: a serial dependence chain, so there is no
-// bandwidth roofline here — the figure of merit is cycles per event.  The warp
-// loads 32 events at a time (coalesced), broadcasts them one by one with
-// shuffles, scores the current table with one packed key per lane and reduces
-// with CREDUX.MIN (__reduce_min_sync).  `live` (device currently held by each
-// ALLOC event, -1 otherwise) sits in shared memory when it fits, else in HBM;
-// only lane 0 touches it, so program order gives consistency.
-constexpr int kReplaySmemEvents = 200 * 1024;
-
-__global__ void __launch_bounds__(32)
-replay_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const int32_t* __restrict__ ev_a,
-              const int32_t* __restrict__ ev_b, long long E, int32_t* __restrict__ out_idx,
-              signed char* __restrict__ live_global) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    signed char* live = (E <= kReplaySmemEvents) ? reinterpret_cast<signed char*>(smem_raw) : live_global;
-    const int lane = threadIdx.x;
-    const int D = st->D;
-    const int d0 = lane, d1 = lane + 32;
-    int32_t fc0 = d0 < D ? st->free_core[d0] : -1;
-    int32_t fm0 = d0 < D ? st->free_mem[d0] : -1;
-    int32_t fc1 = d1 < D ? st->free_core[d1] : -1;
-    int32_t fm1 = d1 < D ? st->free_mem[d1] : -1;
-
-    for (long long base = 0; base < E; base += 32) {
-        const long long i = base + lane;
-        int32_t k = -1, a = 0, b = 0, ta = 0, tb = 0;
-        bool tvalid = false;
-        if (i < E) {
-            k = kind[i];
-            a = ev_a[i];
-            b = ev_b[i];
-            if (k == 1 && a >= 0 && a < i) {  // gather the released event's request now
-                tvalid = kind[a] == 0;
-                ta = ev_a[a];
-                tb = ev_b[a];
-            }
-        }
-        int32_t my_out = -1;
-        const int n = (E - base) < 32 ? static_cast<int>(E - base) : 32;
-        for (int j = 0; j < n; ++j) {
-            const int32_t kj = __shfl_sync(0xffffffffu, k, j);
-            const int32_t aj = __shfl_sync(0xffffffffu, a, j);
-            const int32_t bj = __shfl_sync(0xffffffffu, b, j);
-            int32_t res = -1;
-            if (kj == 0) {
-                const int32_t lc0 = fc0 - aj, lm0 = fm0 - bj;
-                const int32_t lc1 = fc1 - aj, lm1 = fm1 - bj;
-                const bool valid = (aj | bj) >= 0;
-                int32_t key = 0x7fffffff;
-                if (valid && (lc0 | lm0) >= 0 && fc0 >= 0) key = (lc0 << 24) | (lm0 << 6) | d0;
-                if (valid && (lc1 | lm1) >= 0 && fc1 >= 0) key = min(key, (lc1 << 24) | (lm1 << 6) | d1);
-                const int32_t best = __reduce_min_sync(0xffffffffu, key);
-                if (best != 0x7fffffff) {
-                    res = best & 63;
-                    if (res == d0) { fc0 -= aj; fm0 -= bj; }
-                    if (res == d1) { fc1 -= aj; fm1 -= bj; }
-                }
-                if (lane == 0) live[base + j] = static_cast<signed char>(res);
-            } else {
-                const bool tv = __shfl_sync(0xffffffffu, static_cast<int>(tvalid), j) != 0;
-                const int32_t taj = __shfl_sync(0xffffffffu, ta, j);
-                const int32_t tbj = __shfl_sync(0xffffffffu, tb, j);
-                int32_t dev = -1;
-                if (lane == 0) {
-                    live[base + j] = -1;
-                    if (kj == 1 && tv) {
-                        dev = live[aj];
-                        live[aj] = -1;
-                    }
-                }
-                dev = __shfl_sync(0xffffffffu, dev, 0);
-                if (dev >= 0) {
-                    if (dev == d0) { fc0 += taj; fm0 += tbj; }
-                    if (dev == d1) { fc1 += taj; fm1 += tbj; }
-                }
-                res = dev;
-            }
-            if (lane == j) my_out = res;
-        }
-        if (i < E) out_idx[i] = my_out;
-    }
-    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    if (d0 < D) { st->free_core[d0] = fc0; st->free_mem[d0] = fm0; sFc[d0] = fc0; sFm[d0] = fm0; }
-    if (d1 < D) { st->free_core[d1] = fc1; st->free_mem[d1] = fm1; sFc[d1] = fc1; sFm[d1] = fm1; }
-    resort_table_cta(st, D, sFc, sFm, sPosDev, lane);
-}
-
-// Sequential mode for D <= 8: the whole table lives in the registers of every lane as packed
-// compare words (guard | free_core | guard | free_mem | device).  K[d] - Q is at once the
-// feasibility test (both guards survive), the ordering key of the spec ((lc, lm, d) with the
-// guards as constant top bits) and the updated table word of the chosen device — so an ALLOC
-// is 8 subtracts, 8 guard tests, a 3-input-min tree and 8 selects, with no cross-lane
-// traffic on the dependence chain.  All lanes compute the same thing; lane 0 keeps `live`
-// and the outputs.  Events are held 32 at a time in registers (lane j = event j of the chunk),
-// broadcast with shuffles; the next chunk is prefetched while the current one is processed.
-__global__ void __launch_bounds__(32)
-replay8_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const int32_t* __restrict__ ev_a,
-               const int32_t* __restrict__ ev_b, long long E, int32_t* __restrict__ out_idx,
-               signed char* __restrict__ live_global) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    signed char* live = (E <= kReplaySmemEvents) ? reinterpret_cast<signed char*>(smem_raw) : live_global;
-    const int lane = threadIdx.x;
-    const int D = st->D;
-    uint32_t K[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d)
-        K[d] = d < D ? (pack_table_word(st->free_core[d], st->free_mem[d]) | static_cast<uint32_t>(d)) : kPadWord;
-
-    auto fetch = [&](long long i, int32_t& k, uint32_t& q, uint32_t& qt, int32_t& t) {
-        k = -1; q = 0; qt = 0; t = -1;
-        if (i < E) {
-            k = kind[i];
-            const int32_t a = ev_a[i], b = ev_b[i];
-            q = pack_request_word(a, b);
-            if (k == 1 && a >= 0 && a < i && kind[a] == 0) {  // FREE of an earlier ALLOC: fetch its request now
-                t = a;
-                qt = pack_request_word(ev_a[a], ev_b[a]);
-            }
-        }
-    };
-    int32_t nk; uint32_t nq, nqt; int32_t nt;
-    fetch(lane, nk, nq, nqt, nt);
-    for (long long base = 0; base < E; base += 32) {
-        // this chunk's events stay in registers (lane j holds event base + j) and are broadcast
-        // with shuffles, which do not sit on the dependence chain; `live` is lane 0's alone
-        const int32_t ck = nk, ct = nt;
-        const uint32_t cq = nq, cqt = nqt;
-        fetch(base + 32 + lane, nk, nq, nqt, nt);  // prefetch the next chunk
-        const int n = (E - base) < 32 ? static_cast<int>(E - base) : 32;
-        int32_t my_out = -1;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-            const int32_t kj = __shfl_sync(0xffffffffu, ck, j);
-            const uint32_t q = __shfl_sync(0xffffffffu, cq, j);
-            int32_t res = -1;
-            if (kj == 0) {
-                uint32_t w[8], key[8];
-#pragma unroll
-                for (int d = 0; d < 8; ++d) {
-                    w[d] = K[d] - q;
-                    key[d] = ((w[d] & kGuards) == kGuards) ? w[d] : 0xFFFFFFFFu;
-                }
-                const uint32_t best = __vimin3_u32(__vimin3_u32(key[0], key[1], key[2]), __vimin3_u32(key[3], key[4], key[5]),
-                                                   min(key[6], key[7]));
-                if (best != 0xFFFFFFFFu) {
-                    res = static_cast<int32_t>(best & 31u);
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) K[d] = (w[d] == best) ? w[d] : K[d];
-                }
-                if (lane == 0) live[base + j] = static_cast<signed char>(res);
-            } else {
-                const int32_t t = __shfl_sync(0xffffffffu, ct, j);
-                const uint32_t qt = __shfl_sync(0xffffffffu, cqt, j);
-                int32_t dev = -1;
-                if (lane == 0) {
-                    live[base + j] = -1;
-                    if (t >= 0) {
-                        dev = live[t];
-                        live[t] = -1;
-                    }
-                }
-                dev = __shfl_sync(0xffffffffu, dev, 0);
-                if (dev >= 0) {
-#pragma unroll
-                    for (int d = 0; d < 8; ++d) K[d] = (d == dev) ? K[d] + qt : K[d];
-                    res = dev;
-                }
-            }
-            if (lane == j) my_out = res;
-        }
-        if (base + lane < E) out_idx[base + lane] = my_out;
-    }
-    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    if (lane < D) {
-        uint32_t k = 0;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) k = (d == lane) ? K[d] : k;
-        const int32_t fc = static_cast<int32_t>((k >> 24) & 0x7Fu), fm = static_cast<int32_t>((k >> 5) & 0x3FFFFu);
-        st->free_core[lane] = fc;
-        st->free_mem[lane] = fm;
-        sFc[lane] = fc;
-        sFm[lane] = fm;
-    }
-    resort_table_cta(st, D, sFc, sFm, sPosDev, lane);
-}
-
-}  // namespace egpu
+#include "egpu_scan.cuh"
+#include "egpu_replay.cuh"
 
 // =============================================================================
 // Host side: context + C ABI
@@ -1159,13 +130,22 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         {reinterpret_cast<uintptr_t>(d_delta), reinterpret_cast<uintptr_t>(d_delta) + (d_delta ? sizeof(long long) * 2 * ctx->D : 0)},
         {reinterpret_cast<uintptr_t>(d_table_out), reinterpret_cast<uintptr_t>(d_table_out) + (d_table_out ? sizeof(int32_t) * 3 * ctx->D : 0)}};
     bool pipelined = !grid_variant && finalize && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan &&
-                     !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0 &&
-                     ctx->group_len < ctx->pipe_group;
+                     !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0;
     for (int i = 0; pipelined && i < 3 * ctx->group_len; ++i)
         for (int k = 0; k < 3; ++k)
             if (mine[k].lo < ctx->group_out[i].hi && ctx->group_out[i].lo < mine[k].hi) pipelined = false;
-    if (pipelined) flags |= kFlagLateWait;
-    else ctx->group_len = 0;
+    if (pipelined) {
+        flags |= kFlagLateWait;
+        if (ctx->group_len >= ctx->pipe_group) {
+            // group boundary: this launch still scans alongside its predecessors, but it waits
+            // for them before its epilogue and only then lets its successors start; it becomes
+            // the first member of the next group
+            flags |= kFlagBoundary;
+            ctx->group_len = 0;
+        }
+    } else {
+        ctx->group_len = 0;
+    }
     // Early trigger (griddepcontrol.launch_dependents before the work is done) only helps when
     // the next launch is another scan of a pipelined stream, so only those launches do it.
     // (Checked on B200, scripts/probes/pdl_event_probe.cu and scripts/eager_probe.py: events

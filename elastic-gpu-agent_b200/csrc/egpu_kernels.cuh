@@ -47,6 +47,10 @@ constexpr int kFlagLateWait = 4;  // programmatic dependent launch: this launch 
                                   // successor at once and waits for its predecessor only
                                   // before it exits (stream order is kept, nothing else)
 
+constexpr int kFlagBoundary = 16;     // with kFlagLateWait: group boundary of a pipelined stream - scan
+                                      // alongside the predecessors, but wait for them BEFORE the epilogue
+                                      // and only then trigger: everything older is complete when the next
+                                      // group starts, which bounds the launches in flight
 constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before the scan: only on
                                       // streams the caller declared pipelined (EGPU_F_INPUTS_READY)
 
