@@ -33,6 +33,8 @@ VARIANT_LUT = 3
 
 F_COMMIT = 1
 F_INPUTS_READY = 2
+F_PREFIX_COMMIT = 4
+IDX_DEFERRED = -2
 
 EV_ALLOC = 0
 EV_FREE = 1

@@ -102,8 +102,10 @@ class BestFitAllocator:
         return fc, fm, ov
 
     # -- snapshot mode, host buffers -----------------------------------------
-    def bestfit(self, req_core, req_mem, commit: bool = False, out_idx: np.ndarray | None = None):
-        """Returns (idx int32[R], delta_core int64[D], delta_mem int64[D])."""
+    def bestfit(self, req_core, req_mem, commit: bool = False, out_idx: np.ndarray | None = None,
+                prefix_commit: bool = False):
+        """Returns (idx int32[R], delta_core int64[D], delta_mem int64[D]).  prefix_commit:
+        spec 2.5 - requests beyond a device's capacity come back as -2 (DEFERRED)."""
         rc_, rm_ = _i32(req_core), _i32(req_mem)
         if rc_.shape != rm_.shape or rc_.ndim != 1:
             raise L.EgpuError(L.ERR_INVALID, "bestfit")
@@ -115,7 +117,7 @@ class BestFitAllocator:
         dc = np.zeros(D, dtype=np.int64)
         dm = np.zeros(D, dtype=np.int64)
         rc = self._lib.egpu_bestfit_batch(self._h, _ptr(rc_), _ptr(rm_), R, _ptr(idx), _ptr(dc), _ptr(dm),
-                                          1 if commit else 0)
+                                          (L.F_COMMIT if commit else 0) | (L.F_PREFIX_COMMIT if prefix_commit else 0))
         self._check(rc, "egpu_bestfit_batch")
         return idx, dc, dm
 
@@ -170,8 +172,9 @@ class BestFitAllocator:
 
     # -- snapshot mode, device buffers ---------------------------------------
     def bestfit_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int = 0, d_table_out: int = 0,
-                    commit: bool = False, stream: int | None = None, inputs_ready: bool = False):
-        flags = (L.F_COMMIT if commit else 0) | (L.F_INPUTS_READY if inputs_ready else 0)
+                    commit: bool = False, stream: int | None = None, inputs_ready: bool = False, prefix_commit: bool = False):
+        flags = (L.F_COMMIT if commit else 0) | (L.F_INPUTS_READY if inputs_ready else 0) | \
+                (L.F_PREFIX_COMMIT if prefix_commit else 0)
         rc = self._lib.egpu_bestfit_batch_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
                                               C.c_void_p(d_idx), C.c_void_p(d_delta or None),
                                               C.c_void_p(d_table_out or None), flags,

@@ -75,16 +75,21 @@ void fill_sorted(DevState& h) {
 // chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
                     long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
-                    int rpt_hint = 0, unsigned long long push_step_plus1 = 0) {
+                    int rpt_hint = 0, unsigned long long push_step_plus1 = 0, bool contig = false, int* n_tiles_out = nullptr) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
-    SnapLaunch& l = ctx->snap[grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
+    if (contig && grid_variant) return EGPU_ERR_STATE;  // the literal variant has no prefix-commit mode
+    SnapLaunch& l = ctx->snap[contig ? (lut_variant ? 4 : 3) : grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
     if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
         int per_sm = 0;
         if (lut_variant) {
             const int share = ctx->lut_share;
-            if (ctx->lut_threads == 256) {
+            if (contig) {
+                l.lut_fn = bestfit_lut_kernel<256, 4, true>;
+                l.threads = 256;
+                l.smem = sizeof(LutSmem<256, 4>);
+            } else if (ctx->lut_threads == 256) {
                 l.lut_fn = share == 2 ? bestfit_lut_kernel<256, 2> : share == 8 ? bestfit_lut_kernel<256, 8> : bestfit_lut_kernel<256, 4>;
                 l.threads = 256;
                 l.smem = share == 2 ? sizeof(LutSmem<256, 2>) : share == 8 ? sizeof(LutSmem<256, 8>) : sizeof(LutSmem<256, 4>);
@@ -99,6 +104,10 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
             l = pick_launch(ctx->D, grid_variant);
+            if (contig) {
+                l.fn = bucket == 0 ? bestfit_sorted_kernel<8, 256, true> : bucket == 1 ? bestfit_sorted_kernel<16, 256, true>
+                       : bucket == 2 ? bestfit_sorted_kernel<32, 256, true> : bestfit_sorted_kernel<64, 128, true>;
+            }
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
         }
@@ -129,7 +138,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         {reinterpret_cast<uintptr_t>(d_idx), reinterpret_cast<uintptr_t>(d_idx) + static_cast<uintptr_t>(R) * sizeof(int32_t)},
         {reinterpret_cast<uintptr_t>(d_delta), reinterpret_cast<uintptr_t>(d_delta) + (d_delta ? sizeof(long long) * 2 * ctx->D : 0)},
         {reinterpret_cast<uintptr_t>(d_table_out), reinterpret_cast<uintptr_t>(d_table_out) + (d_table_out ? sizeof(int32_t) * 3 * ctx->D : 0)}};
-    bool pipelined = !grid_variant && finalize && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan &&
+    bool pipelined = !grid_variant && !contig && finalize && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan &&
                      !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0;
     for (int i = 0; pipelined && i < 3 * ctx->group_len; ++i)
         for (int k = 0; k < 3; ++k)
@@ -187,12 +196,24 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    unsigned long long* tile_sums = nullptr;
+    if (contig) {  // one tile per CTA: make room for their sums
+        if (want > ctx->tile_cap) {
+            cudaFree(ctx->d_tile_sums);
+            ctx->d_tile_sums = nullptr;
+            ctx->tile_cap = 0;
+            EGPU_CUDA(ctx, cudaMalloc(&ctx->d_tile_sums, sizeof(unsigned long long) * 2 * kMaxD * static_cast<size_t>(want)));
+            ctx->tile_cap = want;
+        }
+        tile_sums = ctx->d_tile_sums;
+        if (n_tiles_out) *n_tiles_out = static_cast<int>(want);
+    }
     if (lut_variant)
         EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.lut_fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
-                                          d_delta, d_table_out, flags, slot, static_cast<const DevLut*>(ctx->d_lut)));
+                                          d_delta, d_table_out, flags, slot, static_cast<const DevLut*>(ctx->d_lut), tile_sums));
     else
         EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, d_rc, d_rm, static_cast<long long>(R), d_idx,
-                                          d_delta, d_table_out, flags, slot));
+                                          d_delta, d_table_out, flags, slot, tile_sums));
     if (flags & kFlagCommit) ctx->lut_dirty = true;
     ctx->launches += 1;
     ctx->seq += 1;
@@ -201,6 +222,30 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     ctx->prev_is_scan = finalize;
     ctx->prev_changes_table = (flags & kFlagCommit) != 0;
     ctx->prev_stream = s;
+    return EGPU_OK;
+}
+
+// Prefix-commit pipeline on device buffers (spec 2.5): CONTIG scan -> per-device cut ->
+// rewrite of the deferred indices -> delta / table' of the committed rows only.
+int launch_prefix_commit(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
+                         long long* d_delta, int32_t* d_table_out, int user_flags, cudaStream_t s) {
+    if (!ctx->d_prefix_out) EGPU_CUDA(ctx, cudaMalloc(&ctx->d_prefix_out, sizeof(PrefixOut)));
+    int n_tiles = 0;
+    // the scan itself must neither publish nor commit: its sums are the uncapped ones
+    int rc = launch_snapshot(ctx, d_rc, d_rm, R, d_idx, nullptr, nullptr, 0, true, s, 0, 0, true, &n_tiles);
+    if (rc != EGPU_OK) return rc;
+    PrefixOut* pf = static_cast<PrefixOut*>(ctx->d_prefix_out);
+    prefix_cut_kernel<<<ctx->D, 256, 0, s>>>(ctx->d_state, d_idx, d_rc, d_rm, R, n_tiles, ctx->d_tile_sums, pf);
+    int64_t blocks = (R + 1023) / 1024;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    prefix_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pf, ctx->D, R, d_idx);
+    prefix_finalize_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, pf, d_delta, d_table_out, (user_flags & EGPU_F_COMMIT) ? 1 : 0);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    ctx->prev_is_scan = false;
+    if (user_flags & EGPU_F_COMMIT) ctx->lut_dirty = true;
     return EGPU_OK;
 }
 
@@ -363,6 +408,8 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
     for (int r = 0; r < kMaxRanks; ++r)
         if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
     cudaFree(ctx->d_xchg);
+    cudaFree(ctx->d_tile_sums);
+    cudaFree(ctx->d_prefix_out);
     cudaFree(ctx->arena);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_lut);
@@ -464,6 +511,9 @@ int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32
     if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (flags & EGPU_F_PREFIX_COMMIT)
+        return launch_prefix_commit(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta), d_table_out,
+                                    flags, s);
     return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta),
                            d_table_out, flags, true, s);
 }
@@ -485,10 +535,11 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
     const int32_t* zc = R > 0 ? static_cast<const int32_t*>(mapped_alias(req_core)) : nullptr;
     const int32_t* zm = R > 0 ? static_cast<const int32_t*>(mapped_alias(req_mem)) : nullptr;
     int32_t* zi = R > 0 ? static_cast<int32_t*>(mapped_alias(out_idx)) : nullptr;
-    if (zc && zm && zi && aligned16(zc) && aligned16(zm) && aligned16(zi) && !ctx->no_zero_copy) {
+    const bool prefix = (commit & EGPU_F_PREFIX_COMMIT) != 0;  // `commit` carries EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT
+    if (!prefix && zc && zm && zi && aligned16(zc) && aligned16(zm) && aligned16(zi) && !ctx->no_zero_copy) {
         // 64 rows per thread: few CTAs, many trips, so reads of later rows and writes of
         // earlier ones are on the link at the same time (PCIe is full duplex)
-        rc = launch_snapshot(ctx, zc, zm, R, zi, ctx->h_delta_dev, nullptr, commit ? EGPU_F_COMMIT : 0, true, s, 64);
+        rc = launch_snapshot(ctx, zc, zm, R, zi, ctx->h_delta_dev, nullptr, (commit & EGPU_F_COMMIT) ? EGPU_F_COMMIT : 0, true, s, 64);
         if (rc != EGPU_OK) return rc;
         EGPU_CUDA(ctx, cudaStreamSynchronize(s));
     } else {
@@ -498,8 +549,10 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
             EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
             EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
         }
-        rc = launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
-                             commit ? EGPU_F_COMMIT : 0, true, s);
+        rc = prefix ? launch_prefix_commit(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
+                                           (commit & EGPU_F_COMMIT) ? EGPU_F_COMMIT : 0, s)
+                    : launch_snapshot(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, ctx->d_delta, nullptr,
+                                      (commit & EGPU_F_COMMIT) ? EGPU_F_COMMIT : 0, true, s);
         if (rc != EGPU_OK) return rc;
         if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
         EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_delta, ctx->d_delta, sizeof(long long) * 2 * D, cudaMemcpyDeviceToHost, s));

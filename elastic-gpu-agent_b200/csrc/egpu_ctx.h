@@ -13,10 +13,10 @@
 using namespace egpu;  // internal header: the context is made of the kernels' types
 
 using SnapKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
-                            unsigned long long);
+                            unsigned long long, unsigned long long*);
 
 using LutKernel = void (*)(egpu::DevState*, const int32_t*, const int32_t*, long long, int32_t*, long long*, int32_t*, int,
-                           unsigned long long, const egpu::DevLut*);
+                           unsigned long long, const egpu::DevLut*, unsigned long long*);
 
 struct SnapLaunch {
     SnapKernel fn = nullptr;
@@ -28,7 +28,10 @@ struct SnapLaunch {
 
 struct egpu_ctx {
     std::mutex mu;
-    SnapLaunch snap[3][4];            // [sorted, grid, lut][D bucket]
+    SnapLaunch snap[5][4];            // [sorted, grid, lut, sorted CONTIG, lut CONTIG][D bucket]
+    unsigned long long* d_tile_sums = nullptr;  // prefix-commit: per-tile per-device sums [tiles][2*64]
+    int64_t tile_cap = 0;
+    void* d_prefix_out = nullptr;     // PrefixOut
     DevLut* d_lut = nullptr;
     XchgBuf* d_xchg = nullptr;        // this rank's exchange buffer (exported to the peers over CUDA IPC)
     void* peer_open[kMaxRanks] = {};  // peers' buffers as opened here (nullptr for own rank)

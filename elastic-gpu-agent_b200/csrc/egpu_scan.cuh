@@ -120,7 +120,8 @@ template <int WARPS>
 __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
                                                  int32_t* sFc, int32_t* sFm, int32_t* sPosDev, int* sLast,
                                                  DevState* st, int D, long long* __restrict__ delta_out,
-                                                 int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+                                                 int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                                                 unsigned long long* __restrict__ tile_sums = nullptr) {
     // slot_step: bits 0..7 = epilogue slot of this launch; bits 8.. = step + 1 when the demand
     // vector must also be pushed to the peers' exchange buffers (0 = single GPU)
     DevState::EpiSlot& ep = st->epi[slot_step & 0xffu];
@@ -132,6 +133,8 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) tot += wacc[w * wstride + j];
         if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
+        // prefix-commit mode: this CTA owns a contiguous run of rows; keep its sums per device
+        if (tile_sums) tile_sums[static_cast<size_t>(blockIdx.x) * 2 * kMaxD + (tid < D ? tid : kMaxD + (tid - D))] = tot;
         __threadfence();  // only the threads that published sums need to order them before the ticket
     }
     __syncthreads();
@@ -200,7 +203,8 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
 template <int DT, int THREADS>
 __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
                                                   long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+                                                  int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                                                  unsigned long long* __restrict__ tile_sums = nullptr) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -220,14 +224,18 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&s.sWarpAcc[0][0], 2 * DT, 0, DT, s.sFc, s.sFm, s.sPosDev, &s.sLast, st, D, delta_out,
-                                   table_out, flags, slot_step);
+                                   table_out, flags, slot_step, tile_sums);
 }
 
-template <int DT, int THREADS>
+// CONTIG = false: vectors are dealt round-robin over the whole grid (the product mapping).
+// CONTIG = true (prefix-commit mode): CTA b scans the contiguous rows of "tile" b and leaves
+// its per-device sums in tile_sums[b][*]; everything else is the same kernel.
+template <int DT, int THREADS, bool CONTIG = false>
 __global__ void __launch_bounds__(THREADS)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                      unsigned long long* __restrict__ tile_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -238,9 +246,16 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
     if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
 
-    const long long nvec = R >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+    long long nvec = R >> 2;  // CONTIG: end of this CTA's tile
+    long long stride = static_cast<long long>(gridDim.x) * THREADS;
     long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+    if (CONTIG) {
+        const long long per = (nvec + gridDim.x - 1) / gridDim.x;
+        const long long lo = static_cast<long long>(blockIdx.x) * per;
+        nvec = (lo + per < nvec) ? lo + per : nvec;
+        stride = THREADS;
+        v = lo + tid;
+    }
 
     // issue the first tile's loads before anything else: the request stream is
     // the only HBM traffic that matters
@@ -304,16 +319,16 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         has1 = nhas1;
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
-    // ragged tail: R % 4 rows, scalar
-    if (blockIdx.x == 0 && tid < static_cast<int>(R & 3)) {
-        const long long r = (nvec << 2) + tid;
+    // ragged tail: R % 4 rows, scalar (they are the LAST rows: in CONTIG mode they belong to the last tile)
+    if (blockIdx.x == (CONTIG ? gridDim.x - 1 : 0) && tid < static_cast<int>(R & 3)) {
+        const long long r = ((R >> 2) << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
     if (boundary) {  // everything older must be complete before the next group may start
         pdl_wait();
         pdl_trigger();
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step, CONTIG ? tile_sums : nullptr);
     if (late && !boundary) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
 }
 
@@ -408,7 +423,8 @@ template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                     const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step) {
+                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                    unsigned long long* __restrict__ /*tile_sums: not supported by the literal variant*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -537,12 +553,12 @@ struct LutSmem {
     alignas(16) unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];  // zeroed with 128-bit stores
 };
 
-template <int THREADS, int SHARE>
+template <int THREADS, int SHARE, bool CONTIG = false>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
-                   const DevLut* __restrict__ glut) {
+                   const DevLut* __restrict__ glut, unsigned long long* __restrict__ tile_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& sm = *reinterpret_cast<LutSmem<THREADS, SHARE>*>(smem_raw);
     constexpr int LW = 32 / SHARE;  // accumulator columns per warp
@@ -556,9 +572,16 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     if (!late) pdl_wait();
     if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
 
-    const long long nvec = R >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * THREADS;
+    long long nvec = R >> 2;
+    long long stride = static_cast<long long>(gridDim.x) * THREADS;
     long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+    if (CONTIG) {
+        const long long per = (nvec + gridDim.x - 1) / gridDim.x;
+        const long long lo = static_cast<long long>(blockIdx.x) * per;
+        nvec = (lo + per < nvec) ? lo + per : nvec;
+        stride = THREADS;
+        v = lo + tid;
+    }
     int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
     bool has0 = v < nvec, has1 = (v + stride) < nvec;
     if (has0) {
@@ -665,9 +688,9 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         has1 = nhas1;
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
-    if (blockIdx.x == 0 && warp == 0) {  // ragged tail: R % 4 rows; whole warp takes part in accumulate()
+    if (blockIdx.x == (CONTIG ? gridDim.x - 1 : 0) && warp == 0) {  // ragged tail: R % 4 rows (the last ones)
         const bool mine = lane < static_cast<int>(R & 3);
-        const long long r = (nvec << 2) + lane;
+        const long long r = ((R >> 2) << 2) + lane;
         const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
         const int32_t idx = lookup(c, m);
         accumulate4(make_int4(idx, -1, -1, -1), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0));
@@ -697,7 +720,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
-                                   delta_out, table_out, flags, slot_step);
+                                   delta_out, table_out, flags, slot_step, CONTIG ? tile_sums : nullptr);
     if (late && !boundary) pdl_wait();
 }
 
@@ -814,5 +837,192 @@ apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus
     }
 }
 
+
+// =============================================================================
+// Prefix-commit (spec 2.5): turn the snapshot choice into an allocation that never
+// oversubscribes
+// =============================================================================
+//
+// Row r with choice d commits iff the running demand of d over rows <= r (all rows that
+// chose d, committed or not) still fits free[d]; otherwise it is DEFERRED (-2).  Demands are
+// non-negative, so per device the running demand is monotone and the rule is a single cut:
+// rows before cut[d] commit, rows from cut[d] on are deferred.  The scan runs in CONTIG mode
+// (CTA b = contiguous tile b) and leaves per-tile per-device sums; one CTA per device then
+// (1) scans the tile sums to find the tile where its device crosses capacity, (2) scans
+// that one tile's rows in order for the exact cut row and the committed demand;
+// prefix_apply_kernel rewrites the indices, prefix_finalize_kernel publishes delta / table'.
+struct PrefixOut {
+    long long cut[kMaxD];          // first deferred row of device d, R when none
+    long long committed_c[kMaxD];  // demand of the committed rows
+    long long committed_m[kMaxD];
+};
+
+// exclusive block scan of two 64-bit values; returns the block totals through tot_*
+template <int THREADS>
+__device__ __forceinline__ void block_scan2(unsigned long long& a, unsigned long long& b, unsigned long long* sh /*[2][THREADS/32]*/,
+                                            unsigned long long& tot_a, unsigned long long& tot_b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ya = __shfl_up_sync(0xffffffffu, ia, o), yb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ya; ib += yb; }
+    }
+    if (lane == 31) { sh[warp] = ia; sh[THREADS / 32 + warp] = ib; }
+    __syncthreads();
+    unsigned long long wa = 0, wb = 0;
+    tot_a = 0; tot_b = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        if (w < warp) { wa += sh[w]; wb += sh[THREADS / 32 + w]; }
+        tot_a += sh[w]; tot_b += sh[THREADS / 32 + w];
+    }
+    __syncthreads();
+    a = ia - a + wa;  // exclusive
+    b = ib - b + wb;
+}
+
+__global__ void __launch_bounds__(256)
+prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ idx, const int32_t* __restrict__ req_core,
+                  const int32_t* __restrict__ req_mem, long long R, int n_tiles,
+                  const unsigned long long* __restrict__ tile_sums, PrefixOut* __restrict__ out) {
+    constexpr int T = 256;
+    __shared__ unsigned long long sh[2 * (T / 32)];
+    __shared__ long long sCutTile, sCutRow;
+    __shared__ unsigned long long sBaseC, sBaseM, sComC, sComM;
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned long long cap_c = static_cast<unsigned long long>(st->free_core[d]);
+    const unsigned long long cap_m = static_cast<unsigned long long>(st->free_mem[d]);
+    if (tid == 0) { sCutTile = n_tiles; sCutRow = R; sBaseC = 0; sBaseM = 0; sComC = 0; sComM = 0; }
+    __syncthreads();
+    // (1) which tile crosses capacity?
+    unsigned long long run_c = 0, run_m = 0;
+    for (int t0 = 0; t0 < n_tiles; t0 += T) {
+        const int t = t0 + tid;
+        unsigned long long c = t < n_tiles ? tile_sums[static_cast<size_t>(t) * 2 * kMaxD + d] : 0ull;
+        unsigned long long m = t < n_tiles ? tile_sums[static_cast<size_t>(t) * 2 * kMaxD + kMaxD + d] : 0ull;
+        const unsigned long long own_c = c, own_m = m;
+        unsigned long long tot_c, tot_m;
+        block_scan2<T>(c, m, sh, tot_c, tot_m);  // c, m = demand of the tiles before t within this pass
+        const unsigned long long before_c = run_c + c, before_m = run_m + m;
+        // demand is monotone: exactly one tile has "fits before it, does not fit after it"
+        if (t < n_tiles && (before_c + own_c > cap_c || before_m + own_m > cap_m) && before_c <= cap_c && before_m <= cap_m)
+            sCutTile = t;
+        __syncthreads();
+        if (sCutTile < n_tiles) break;
+        run_c += tot_c;
+        run_m += tot_m;
+    }
+    __syncthreads();
+    const long long cut_tile = sCutTile;
+    if (cut_tile >= n_tiles) {  // the device never fills up: everything that chose it commits
+        if (tid == 0) {
+            out->cut[d] = R;
+            out->committed_c[d] = static_cast<long long>(run_c);
+            out->committed_m[d] = static_cast<long long>(run_m);
+        }
+        return;
+    }
+    // demand before the cut tile: rescan (cheap) up to cut_tile with a plain strided sum
+    {
+        unsigned long long c = 0, m = 0;
+        for (long long t = tid; t < cut_tile; t += T) {
+            c += tile_sums[static_cast<size_t>(t) * 2 * kMaxD + d];
+            m += tile_sums[static_cast<size_t>(t) * 2 * kMaxD + kMaxD + d];
+        }
+        unsigned long long tc, tm;
+        block_scan2<T>(c, m, sh, tc, tm);
+        if (tid == 0) { sBaseC = tc; sBaseM = tm; }
+        __syncthreads();
+    }
+    // (2) rows of the cut tile, in order
+    const long long nvec = R >> 2;
+    const long long per = (nvec + n_tiles - 1) / n_tiles;
+    const long long row_lo = cut_tile * per * 4;
+    long long row_hi = (cut_tile + 1) * per * 4;
+    if (row_hi > nvec * 4) row_hi = nvec * 4;
+    if (cut_tile == n_tiles - 1) row_hi = R;  // the ragged tail belongs to the last tile
+    unsigned long long base_c = sBaseC, base_m = sBaseM;
+    for (long long r0 = row_lo; r0 < row_hi; r0 += 4 * T) {
+        const long long r = r0 + 4ll * tid;
+        unsigned long long c4[4], m4[4];
+        unsigned long long c = 0, m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool mine = (r + k) < row_hi && idx[r + k] == d;
+            c4[k] = mine ? static_cast<unsigned long long>(req_core[r + k]) : 0ull;
+            m4[k] = mine ? static_cast<unsigned long long>(req_mem[r + k]) : 0ull;
+            c += c4[k];
+            m += m4[k];
+        }
+        unsigned long long tot_c, tot_m;
+        block_scan2<T>(c, m, sh, tot_c, tot_m);
+        unsigned long long pc = base_c + c, pm = base_m + m;  // demand before this thread's first row
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((r + k) < row_hi && idx[r + k] == d) {
+                // monotone demand: exactly one row fits before it and not with it - the cut
+                if ((pc + c4[k] > cap_c || pm + m4[k] > cap_m) && pc <= cap_c && pm <= cap_m) {
+                    sCutRow = r + k;
+                    sComC = pc;
+                    sComM = pm;
+                }
+                pc += c4[k];
+                pm += m4[k];
+            }
+        }
+        __syncthreads();
+        if (sCutRow < R) break;
+        base_c += tot_c;
+        base_m += tot_m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out->cut[d] = sCutRow;
+        out->committed_c[d] = static_cast<long long>(sCutRow < R ? sComC : base_c);
+        out->committed_m[d] = static_cast<long long>(sCutRow < R ? sComM : base_m);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prefix_apply_kernel(const PrefixOut* __restrict__ pf, int D, long long R, int32_t* __restrict__ idx) {
+    __shared__ long long sCut[kMaxD];
+    if (threadIdx.x < kMaxD) sCut[threadIdx.x] = threadIdx.x < D ? pf->cut[threadIdx.x] : 0;
+    __syncthreads();
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < R; r += stride) {
+        const int32_t i = idx[r];
+        if (i >= 0 && r >= sCut[i]) idx[r] = -2;
+    }
+}
+
+__global__ void __launch_bounds__(kMaxD)
+prefix_finalize_kernel(DevState* __restrict__ st, const PrefixOut* __restrict__ pf, long long* __restrict__ delta_out,
+                       int32_t* __restrict__ table_out, int commit) {
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    const int D = st->D;
+    const int d = threadIdx.x;
+    if (d < D) {
+        const long long dc = pf->committed_c[d], dm = pf->committed_m[d];
+        const long long nc = static_cast<long long>(st->free_core[d]) - dc;  // >= 0 by construction
+        const long long nm = static_cast<long long>(st->free_mem[d]) - dm;
+        if (delta_out) {
+            delta_out[d] = dc;
+            delta_out[D + d] = dm;
+        }
+        if (table_out) {
+            table_out[d] = static_cast<int32_t>(nc);
+            table_out[D + d] = static_cast<int32_t>(nm);
+            table_out[2 * D + d] = 0;
+        }
+        if (commit) {
+            st->free_core[d] = static_cast<int32_t>(nc);
+            st->free_mem[d] = static_cast<int32_t>(nm);
+            sFc[d] = static_cast<int32_t>(nc);
+            sFm[d] = static_cast<int32_t>(nm);
+        }
+    }
+    if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, d);
+}
 
 }  // namespace egpu

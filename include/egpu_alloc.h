@@ -91,6 +91,13 @@ extern "C" {
                                     enqueued later on the stream still sees them
                                     complete. */
 
+#define EGPU_F_PREFIX_COMMIT 4   /* spec 2.5: a request commits only while the running demand of
+                                    its device (all earlier requests that chose it) still fits;
+                                    the others get EGPU_IDX_DEFERRED, the demand sums and table'
+                                    count committed requests only, so table' never goes negative.
+                                    Single GPU; not with EGPU_VARIANT_GRID.  In egpu_bestfit_batch
+                                    pass it in `commit` (EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT). */
+
 /* kernel variants for the snapshot scan (egpu_set_variant) */
 #define EGPU_VARIANT_AUTO    0   /* SORTED for D <= 16, LUT above */
 #define EGPU_VARIANT_GRID    1   /* direct (device x request) score grid, min over packed keys */

@@ -72,6 +72,28 @@ def snapshot(free_core, free_mem, req_core, req_mem, chunk: int = 1 << 18):
     return idx, dc, dm, apply_delta(fc, fm, dc, dm)
 
 
+def prefix_commit(free_core, free_mem, req_core, req_mem):
+    """Spec §2.5 written with per-device cumulative sums (independent of the C loop)."""
+    idx, _, _, _ = snapshot(free_core, free_mem, req_core, req_mem)
+    fc = np.asarray(free_core, dtype=np.int64)
+    fm = np.asarray(free_mem, dtype=np.int64)
+    rc = np.asarray(req_core, dtype=np.int64)
+    rm = np.asarray(req_mem, dtype=np.int64)
+    D = fc.size
+    out = idx.copy()
+    dc = np.zeros(D, dtype=np.int64)
+    dm = np.zeros(D, dtype=np.int64)
+    for d in range(D):
+        sel = idx == d
+        pc = np.cumsum(np.where(sel, rc, 0))
+        pm = np.cumsum(np.where(sel, rm, 0))
+        ok = sel & (pc <= fc[d]) & (pm <= fm[d])
+        out[sel & ~ok] = -2
+        dc[d] = rc[ok].sum()
+        dm[d] = rm[ok].sum()
+    return out, dc, dm, apply_delta(fc, fm, dc, dm)
+
+
 def apply_delta(free_core, free_mem, delta_core, delta_mem) -> np.ndarray:
     c = np.asarray(free_core, dtype=np.int64) - np.asarray(delta_core, dtype=np.int64)
     m = np.asarray(free_mem, dtype=np.int64) - np.asarray(delta_mem, dtype=np.int64)

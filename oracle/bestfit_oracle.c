@@ -146,6 +146,40 @@ int oracle_bestfit_snapshot(const int32_t* free_core, const int32_t* free_mem, i
     return 0;
 }
 
+/* Prefix-commit (spec §2.5): the snapshot choice, but request r
+ * commits only while the running demand of its device - over ALL rows <= r that chose it,
+ * committed or not - still fits free[d]; otherwise out_idx[r] = -2 (DEFERRED).  The demand
+ * sums and table' count committed rows only, so table' is never negative. */
+int oracle_bestfit_prefix_commit(const int32_t* free_core, const int32_t* free_mem, int32_t D,
+                                 const int32_t* req_core, const int32_t* req_mem, int64_t R,
+                                 int32_t* out_idx, int64_t* delta_core, int64_t* delta_mem,
+                                 int32_t* table_out) {
+    if (oracle_table_valid(free_core, free_mem, D) != 0 || R < 0) return -1;
+    int64_t run_c[ORACLE_MAX_DEVICES], run_m[ORACLE_MAX_DEVICES], dc[ORACLE_MAX_DEVICES], dm[ORACLE_MAX_DEVICES];
+    memset(run_c, 0, sizeof run_c);
+    memset(run_m, 0, sizeof run_m);
+    memset(dc, 0, sizeof dc);
+    memset(dm, 0, sizeof dm);
+    for (int64_t r = 0; r < R; ++r) {
+        int32_t d = oracle_pick(free_core, free_mem, D, req_core[r], req_mem[r]);
+        if (d >= 0) {
+            run_c[d] += req_core[r];
+            run_m[d] += req_mem[r];
+            if (run_c[d] <= free_core[d] && run_m[d] <= free_mem[d]) {
+                dc[d] += req_core[r];
+                dm[d] += req_mem[r];
+            } else {
+                d = -2;
+            }
+        }
+        out_idx[r] = d;
+    }
+    if (delta_core) memcpy(delta_core, dc, sizeof(int64_t) * (size_t)D);
+    if (delta_mem) memcpy(delta_mem, dm, sizeof(int64_t) * (size_t)D);
+    if (table_out) oracle_apply_delta(free_core, free_mem, D, dc, dm, table_out);
+    return 0;
+}
+
 /* Sequential mode (spec §2.6).  free_core/free_mem are updated in place.
  * kind 0 = ALLOC(core=a, mem=b); kind 1 = FREE(event index a). */
 int oracle_replay(int32_t* free_core, int32_t* free_mem, int32_t D, const int32_t* kind,

@@ -33,6 +33,8 @@ def load() -> C.CDLL:
         lib.oracle_pick_one.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32]
         lib.oracle_bestfit_snapshot.restype = C.c_int
         lib.oracle_bestfit_snapshot.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int]
+        lib.oracle_bestfit_prefix_commit.restype = C.c_int
+        lib.oracle_bestfit_prefix_commit.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp]
         lib.oracle_replay.restype = C.c_int
         lib.oracle_replay.argtypes = [vp, vp, C.c_int32, vp, vp, vp, C.c_int64, vp]
         lib.oracle_device_hash.restype = C.c_int
@@ -98,6 +100,20 @@ def snapshot(free_core, free_mem, req_core, req_mem, nthreads: int = 1):
                                        int(nthreads))
     if r != 0:
         raise ValueError(f"oracle_bestfit_snapshot failed: {r}")
+    return idx, dc, dm, tab
+
+
+def prefix_commit(free_core, free_mem, req_core, req_mem):
+    """(idx with -2 = DEFERRED, delta_core, delta_mem, table_out[3D]) per spec §2.5."""
+    fc, fm, rc, rm = _i32(free_core), _i32(free_mem), _i32(req_core), _i32(req_mem)
+    D, R = fc.size, rc.size
+    idx = np.empty(R, dtype=np.int32)
+    dc = np.zeros(D, dtype=np.int64)
+    dm = np.zeros(D, dtype=np.int64)
+    tab = np.zeros(3 * D, dtype=np.int32)
+    r = load().oracle_bestfit_prefix_commit(_p(fc), _p(fm), D, _p(rc), _p(rm), R, _p(idx), _p(dc), _p(dm), _p(tab))
+    if r != 0:
+        raise ValueError(f"oracle_bestfit_prefix_commit failed: {r}")
     return idx, dc, dm, tab
 
 

@@ -157,6 +157,73 @@ def test_packed_wire_format(D, alloc, oracle_c, egpu):
                 alloc.host_free(a.ctypes.data)
 
 
+@pytest.mark.parametrize("case", KAT["prefix_commit"], ids=lambda c: c["name"])
+def test_prefix_commit_kat(case, alloc):
+    for variant in (2, 3):
+        alloc.set_variant(variant)
+        alloc.set_table(case["free_core"], case["free_mem"])
+        idx, dc, dm = alloc.bestfit(case["req_core"], case["req_mem"], commit=True, prefix_commit=True)
+        assert idx.tolist() == case["idx"]
+        assert dc.tolist() == case["delta_core"] and dm.tolist() == case["delta_mem"]
+        fc, fm, ov = alloc.table()
+        assert fc.tolist() == case["table_core"] and fm.tolist() == case["table_mem"] and not ov.any()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("D,R", [(1, 5), (8, 1000), (8, 70_003), (9, 40_001), (64, 70_003), (64, 1_000_003), (8, 4_000_001)])
+def test_prefix_commit_matches_oracle(D, R, variant, alloc, oracle_c):
+    rng = np.random.default_rng(31 * D + R)
+    fc = rng.integers(0, 101, D).astype(np.int32)
+    fm = rng.integers(0, 1 << 18, D).astype(np.int32)
+    # small requests, so that the cut of each device falls somewhere inside the batch
+    rc = rng.integers(0, 3, R).astype(np.int32)
+    rm = rng.integers(0, 300, R).astype(np.int32)
+    rc[rng.integers(0, R, max(1, R // 50))] = rng.integers(-1, 120, max(1, R // 50))
+    alloc.set_variant(variant)
+    alloc.set_table(fc, fm)
+    idx, dc, dm = alloc.bestfit(rc, rm, prefix_commit=True)
+    o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(fc, fm, rc, rm)
+    assert np.array_equal(idx, o_idx)
+    assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+    g_c, g_m, _ = alloc.table()
+    assert np.array_equal(g_c, fc) and np.array_equal(g_m, fm)  # no commit asked
+
+
+def test_prefix_commit_retry_rounds_fill_the_node(alloc, oracle_c, egpu):
+    """The caller's loop of spec 2.5: commit what fits, re-score the deferred rows against the
+    new table, until nothing is deferred.  Every round must match the oracle and the table must
+    never go negative."""
+    import torch
+    fc, fm = egpu.synth.table_full(8)
+    rc, rm = egpu.synth.requests(2, 123, 3000)   # cfg2 sizes: 5..100 % core
+    alloc.set_table(fc, fm)
+    cur_c, cur_m = fc.copy(), fm.copy()
+    pend = np.arange(rc.size)
+    placed = np.full(rc.size, -9, dtype=np.int32)
+    for rounds in range(1, 50):
+        idx, dc, dm = alloc.bestfit(rc[pend], rm[pend], commit=True, prefix_commit=True)
+        o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(cur_c, cur_m, rc[pend], rm[pend])
+        assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+        cur_c, cur_m = o_tab[:8].copy(), o_tab[8:16].copy()
+        g_c, g_m, ov = alloc.table()
+        assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m) and not ov.any() and (g_c >= 0).all()
+        placed[pend[idx != -2]] = idx[idx != -2]
+        pend = pend[idx == -2]
+        if pend.size == 0:
+            break
+    assert pend.size == 0 and rounds < 49
+    # the node ends up (nearly) full of core: whatever is left cannot hold the smallest request that failed
+    assert (placed >= -1).all()
+
+
+def test_prefix_commit_not_with_grid_variant(alloc, egpu):
+    alloc.set_variant(1)
+    alloc.set_table([10], [10])
+    with pytest.raises(egpu.EgpuError) as ei:
+        alloc.bestfit([1], [1], prefix_commit=True)
+    assert ei.value.code == -6
+
+
 def test_ties_pick_lowest_index_everywhere(alloc):
     for D in (8, 64):
         alloc.set_table([100] * D, [1000] * D)

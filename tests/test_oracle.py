@@ -44,6 +44,18 @@ def test_sequential_kat(case, impl, oracle_c, oracle_np):
     assert fm.tolist() == case["table_mem"]
 
 
+@pytest.mark.parametrize("case", KAT["prefix_commit"], ids=lambda c: c["name"])
+@pytest.mark.parametrize("impl", ["c", "np"])
+def test_prefix_commit_kat(case, impl, oracle_c, oracle_np):
+    o = oracle_c if impl == "c" else oracle_np
+    idx, dc, dm, tab = o.prefix_commit(case["free_core"], case["free_mem"], case["req_core"], case["req_mem"])
+    D = len(case["free_core"])
+    assert idx.tolist() == case["idx"]
+    assert dc.tolist() == case["delta_core"] and dm.tolist() == case["delta_mem"]
+    assert tab[:D].tolist() == case["table_core"] and tab[D:2 * D].tolist() == case["table_mem"]
+    assert not tab[2 * D:].any()
+
+
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg3_1m", "cfg4"])
 def test_c_oracle_matches_golden(name, oracle_c, egpu):
     g = SYN["snapshot"][name]
@@ -108,6 +120,28 @@ def test_two_oracles_agree_and_properties(oracle_c, oracle_np, table, rq):
     for d in range(D):
         sel = i1 == d
         assert dc1[d] == int(rc[sel].astype(np.int64).sum()) and dm1[d] == int(rm[sel].astype(np.int64).sum())
+
+
+@settings(max_examples=100, deadline=None)
+@given(tables, reqs)
+def test_prefix_commit_oracles_agree_and_never_oversubscribe(oracle_c, oracle_np, table, rq):
+    fc, fm = table
+    rc = np.array([r[0] for r in rq], dtype=np.int32)
+    rm = np.array([r[1] for r in rq], dtype=np.int32)
+    a = oracle_c.prefix_commit(fc, fm, rc, rm)
+    b = oracle_np.prefix_commit(fc, fm, rc, rm)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    idx, dc, dm, tab = a
+    D = len(fc)
+    assert (tab[:2 * D] >= 0).all() and not tab[2 * D:].any()
+    snap, *_ = oracle_c.snapshot(fc, fm, rc, rm)
+    # deferred rows are exactly snapshot choices that were cut; committed ones keep their choice
+    assert ((idx == snap) | ((idx == -2) & (snap >= 0))).all()
+    for d in range(D):
+        sel = idx == d
+        assert dc[d] == int(rc[sel].astype(np.int64).sum()) <= fc[d]
+        assert dm[d] == int(rm[sel].astype(np.int64).sum()) <= fm[d]
+
 
 
 events = st.lists(st.tuples(st.integers(0, 1), st.integers(-1, 60), st.integers(0, 2000)), min_size=0, max_size=60)
