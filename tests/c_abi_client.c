@@ -1,0 +1,70 @@
+/*
+ * A plain C client of the C ABI, linked against libegpu_alloc.so the way the cgo shim of
+ * INTEGRATION.md would be: no Python, no C++, no CUDA headers.  Runs the cfg1 known-answer
+ * vector, a GetPreferredAllocation call and a device-set hash.
+ * Built and run by tests/test_c_client.py.  Exit code 0 = all checks passed.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "egpu_alloc.h"
+#include "egpu_devhash.h"
+#include "egpu_plugin.h"
+
+#define CHECK(cond, msg)                                  \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            fprintf(stderr, "FAILED: %s\n", msg);         \
+            return 1;                                     \
+        }                                                 \
+    } while (0)
+
+int main(void) {
+    egpu_ctx* ctx = NULL;
+    int rc = egpu_ctx_create(0, &ctx);
+    if (rc == EGPU_ERR_NO_DEVICE) {
+        printf("no CUDA device: %s\n", egpu_strerror(rc));
+        return 77; /* the CPU-side test accepts this: there is no fallback to exercise */
+    }
+    CHECK(rc == EGPU_OK, "egpu_ctx_create");
+    int32_t fc[8], fm[8];
+    for (int d = 0; d < 8; ++d) { fc[d] = 100; fm[d] = 183359; }
+    CHECK(egpu_table_set(ctx, fc, fm, 8) == EGPU_OK, "egpu_table_set");
+
+    /* cfg1, snapshot: five identical requests all pick device 0 and oversubscribe it */
+    int32_t core[5] = {25, 25, 25, 25, 25}, mem[5] = {1024, 1024, 1024, 1024, 1024}, idx[5];
+    int64_t dc[8], dm[8];
+    CHECK(egpu_bestfit_batch(ctx, core, mem, 5, idx, dc, dm, 0) == EGPU_OK, "egpu_bestfit_batch");
+    for (int i = 0; i < 5; ++i) CHECK(idx[i] == 0, "snapshot idx");
+    CHECK(dc[0] == 125 && dm[0] == 5120, "snapshot demand sums");
+
+    /* the same with prefix-commit: the fifth is deferred, the table ends at exactly 0 core */
+    CHECK(egpu_bestfit_batch(ctx, core, mem, 5, idx, dc, dm, EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT) == EGPU_OK, "prefix commit");
+    CHECK(idx[3] == 0 && idx[4] == EGPU_IDX_DEFERRED && dc[0] == 100, "prefix-commit result");
+    int32_t ov[8];
+    CHECK(egpu_table_get(ctx, fc, fm, ov) == EGPU_OK && fc[0] == 0 && fm[0] == 183359 - 4096 && ov[0] == 0, "table after commit");
+
+    /* cfg1, sequential: the deferred request now goes to device 1 */
+    int32_t kind[1] = {EGPU_EV_ALLOC}, a[1] = {25}, b[1] = {1024}, out[1];
+    CHECK(egpu_replay(ctx, kind, a, b, 1, out) == EGPU_OK && out[0] == 1, "egpu_replay");
+
+    /* GetPreferredAllocation: 30 core units of GPU 0 and 25 of GPU 2 available, 25 asked */
+    char ids[55][8];
+    const char* avail[55];
+    int n = 0;
+    for (int j = 0; j < 30; ++j) { egpu_device_id_format(0, 40 + j, ids[n], 8); avail[n] = ids[n]; ++n; }
+    for (int j = 0; j < 25; ++j) { egpu_device_id_format(2, 75 + j, ids[n], 8); avail[n] = ids[n]; ++n; }
+    int32_t pos[25], gpu = -1;
+    CHECK(egpu_preferred_allocation(ctx, avail, n, NULL, 0, 25, EGPU_RESOURCE_CORE, pos, &gpu) == EGPU_OK, "preferred allocation");
+    CHECK(gpu == 2 && strcmp(avail[pos[0]], "2-75") == 0 && strcmp(avail[pos[24]], "2-99") == 0, "preferred allocation picks the exact fit");
+
+    /* types.NewDevice([...]).Hash of {"3-07"} = first 8 hex digits of sha256("3-07") */
+    const char* one[1] = {"3-07"};
+    char h[9];
+    CHECK(egpu_device_hash(ctx, one, 1, h) == EGPU_OK, "egpu_device_hash");
+    printf("hash(3-07) = %s, launches = %lld\n", h, (long long)egpu_launch_count(ctx));
+    egpu_ctx_destroy(ctx);
+    printf("c abi client ok\n");
+    return 0;
+}
