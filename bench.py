@@ -42,7 +42,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "alloc_decisions_per_sec"
 UNIT = "decisions/s"
-APPLY_BATCH = 4  # N > 1: one apply launch covers this many steps' demand vectors
+APPLY_BATCH = 8   # N > 1: one apply launch covers this many steps' demand vectors
+THROTTLE = 16     # N > 1: every THROTTLE steps the scans wait for the applies of two blocks ago (<= 32 steps ahead)
 RING = 16  # batches in the rotation: 16 x 12 MB (1M rows) = 192 MB > 126 MB L2
 
 
@@ -267,19 +268,19 @@ def main():
         elif use_peer:
             # scans stay back to back on the launching stream (they overlap each other); the
             # apply kernels run on a second stream and are ordered by DATA: each waits for the
-            # flags of its step.  Every 8 steps the scans wait for the apply of 8 steps ago,
-            # which keeps a rank within the 32 exchange slots.
+            # flags of its step.  Every THROTTLE steps the scans wait for the apply of THROTTLE
+            # steps ago, which keeps a rank within the 64 exchange slots.
             k = step_no[0]
             step_no[0] += 1
-            if k % 8 == 0 and (k - 8) in apply_done:
-                stream.wait_event(apply_done[k - 8])
+            if k % THROTTLE == 0 and (k - THROTTLE) in apply_done:
+                stream.wait_event(apply_done[k - THROTTLE])
             alloc.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, sh, inputs_ready=True)
             alloc.apply_peers_dev(k, to.data_ptr(), False, apply_stream.cuda_stream)
-            if k % 8 == 0:
+            if k % THROTTLE == 0:
                 ev = torch.cuda.Event()
                 ev.record(apply_stream)
                 apply_done[k] = ev
-                apply_done.pop(k - 16, None)
+                apply_done.pop(k - 2 * THROTTLE, None)
         else:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), delta.data_ptr(), 0, False, sh)
             dist.all_gather_into_tensor(gathered, delta)
@@ -310,24 +311,24 @@ def main():
             with torch.cuda.graph(graph, stream=cap):
                 if use_peer:
                     # two chains in the graph: scans (programmatic edges between them) and
-                    # apply kernels, coupled every 8 steps; step numbers restart at 0 on
+                    # apply kernels, coupled every THROTTLE steps; step numbers restart at 0 on
                     # every replay (the apply kernel consumes the flags, so that is safe)
                     apply_stream.wait_stream(cap)
                     done = {}
                     for k in range(args.steps):
                         c, m, idx, dl, to = ring[k % nb]
-                        if k % 8 == 0 and (k // 8 - 2) in done:
-                            cap.wait_event(done[k // 8 - 2])  # scans run at most 16 steps ahead of the applies
+                        if k % THROTTLE == 0 and (k // THROTTLE - 2) in done:
+                            cap.wait_event(done[k // THROTTLE - 2])  # scans run at most 2 * THROTTLE steps ahead of the applies
                         alloc.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, csh,
                                                 inputs_ready=True)
                         if k % APPLY_BATCH == APPLY_BATCH - 1 or k == args.steps - 1:
                             first = k - (k % APPLY_BATCH)
                             outs = [ring[j % nb][4].data_ptr() for j in range(first, k + 1)]
                             alloc.apply_peers_multi_dev(first, outs, False, apply_stream.cuda_stream)
-                        if k % 8 == 7:
+                        if k % THROTTLE == THROTTLE - 1:
                             ev = torch.cuda.Event()
                             ev.record(apply_stream)
-                            done[k // 8] = ev
+                            done[k // THROTTLE] = ev
                     cap.wait_stream(apply_stream)
                 else:
                     for i in range(args.steps):
@@ -603,7 +604,7 @@ def main():
                        "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
                              if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
                        "launch": ("CUDA graph: K scan launches whose last CTA pushes the demand vector to every peer's memory + "
-                                  "one apply launch per 4 steps on a second stream (no NCCL on the data path)") if (graph is not None and use_peer)
+                                  "one apply launch per 8 steps on a second stream (no NCCL on the data path)") if (graph is not None and use_peer)
                                  else "CUDA graph of K scan launches" if graph is not None else
                                  ("eager launches; demand vectors pushed to peer memory by the scan's last CTA, apply kernels on a second stream"
                                   if use_peer else "eager launches + NCCL all-gather of demand vectors"),

@@ -58,10 +58,10 @@ constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before
 constexpr int kAccShift = 38;
 
 // Multi-GPU exchange of demand vectors through peer memory.  Every rank owns
-// one XchgBuf; rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
+// one XchgBuf (64 slots); rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
 // rank's buffer (plain stores over NVLink), followed by flag = s + 1 with release.sys.
 constexpr int kMaxRanks = 8;
-constexpr int kXchgSlots = 32;
+constexpr int kXchgSlots = 64;
 struct XchgRow {
     long long delta[2 * kMaxD];
     unsigned long long flag;  // step + 1 once delta[] is complete

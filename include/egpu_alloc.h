@@ -194,8 +194,9 @@ int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G,
  *       a release flag - the exchange is fused into the scan kernel;
  *   egpu_table_apply_peers_dev    waits (acquire) until all `world` vectors of `step`
  *       have landed locally, applies their sum: table' (and commit) as in snapshot mode.
- * `step` must increase by one per sharded step on every rank; a rank may run at most
- * 16 steps ahead of its own apply (32 exchange slots).  The scan itself never commits. */
+ * `step` must increase by one per sharded step on every rank; a rank's scans may run at
+ * most 32 steps ahead of its own applies (64 exchange slots: then no peer can be more than
+ * 63 steps ahead of what this rank has consumed).  The scan itself never commits. */
 #define EGPU_IPC_HANDLE_BYTES 64
 #define EGPU_MAX_RANKS 8
 int egpu_peer_export(egpu_ctx* ctx, void* handle_out);

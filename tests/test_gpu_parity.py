@@ -502,6 +502,49 @@ def test_full_size_properties_64mi(alloc, egpu):
     assert torch.equal(delta, torch.cat([dc, dm]))
 
 
+def test_concurrent_callers_share_one_context(alloc, oracle_c, egpu):
+    """grpc-go runs every RPC on its own goroutine, goroutines migrate between OS threads, and
+    the reference serialises commits with one mutex per plugin (pkg/plugins/gpushare.go:114).
+    Here: 6 OS threads hammer ONE context (ctypes drops the GIL); every answer must be exact."""
+    import threading
+    w = egpu.synth.workload("cfg3")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    errors = []
+
+    def worker(k):
+        try:
+            for i in range(25):
+                R = 1000 + 37 * k + i
+                rc, rm = egpu.synth.requests(3, 1000 * k + i, R)
+                idx, dc, dm = alloc.bestfit(rc, rm)
+                o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm)
+                if not (np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)):
+                    errors.append((k, i))
+        except Exception as ex:  # noqa: BLE001
+            errors.append((k, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+
+
+def test_misaligned_device_pointers_are_rejected(alloc, egpu):
+    import torch
+    alloc.set_table([10], [10])
+    c = torch.zeros(64, dtype=torch.int32, device="cuda")
+    m = torch.zeros(64, dtype=torch.int32, device="cuda")
+    o = torch.zeros(64, dtype=torch.int32, device="cuda")
+    for bad in ((4, 0, 0), (0, 8, 0), (0, 0, 12)):
+        with pytest.raises(egpu.EgpuError) as ei:
+            alloc.bestfit_dev(c.data_ptr() + bad[0], m.data_ptr() + bad[1], 8, o.data_ptr() + bad[2])
+        assert ei.value.code == -1
+    alloc.bestfit_dev(c.data_ptr() + 16, m.data_ptr() + 32, 8, o.data_ptr() + 48)  # 16-byte aligned offsets are fine
+    torch.cuda.synchronize()
+
+
 def test_error_paths(alloc, egpu):
     with pytest.raises(egpu.EgpuError) as ei:
         alloc.bestfit([1], [1])

@@ -21,7 +21,7 @@ def test_world1_shard_step_equals_snapshot(alloc, oracle_c, egpu):
     s = torch.cuda.current_stream().cuda_stream
     D, R = 64, 50_003
     cur_c, cur_m = w["free_core"].copy(), w["free_mem"].copy()
-    for step in range(40):  # more steps than exchange slots
+    for step in range(80):  # more steps than exchange slots (64)
         rc, rm = egpu.synth.requests(4, 900 + step, R)
         c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
         idx = torch.empty(R + 1, dtype=torch.int32, device="cuda")
