@@ -42,8 +42,9 @@ import numpy as np  # noqa: E402
 
 METRIC = "alloc_decisions_per_sec"
 UNIT = "decisions/s"
-APPLY_BATCH = 8   # N > 1: one apply launch covers this many steps' demand vectors
-THROTTLE = 16     # N > 1: every THROTTLE steps the scans wait for the applies of two blocks ago (<= 32 steps ahead)
+APPLY_BATCH = int(os.environ.get("EGPU_BENCH_APPLY_BATCH", "8"))   # N > 1: one apply launch covers this many steps' demand vectors
+THROTTLE = int(os.environ.get("EGPU_BENCH_THROTTLE", "16"))       # N > 1: every THROTTLE steps the scans wait for the applies of
+                                                                  # two blocks ago (<= 32 steps ahead; must stay <= 16 for 64 slots)
 RING = 16  # batches in the rotation: 16 x 12 MB (1M rows) = 192 MB > 126 MB L2
 
 
@@ -190,6 +191,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: demand vectors through peer memory fused into the scan (default) or NCCL all-gather")
+    ap.add_argument("--force-peer", action="store_true",
+                    help="experiment: use the peer-exchange step structure even at N = 1 (exchange with self)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -250,19 +253,23 @@ def main():
     torch.cuda.synchronize()
 
     # N > 1, default: exchange fused into the scan through peer memory (CUDA IPC over NVLink)
-    use_peer = world > 1 and args.exchange == "peer"
+    use_peer = (world > 1 and args.exchange == "peer") or args.force_peer
     apply_stream = torch.cuda.Stream() if use_peer else None
     apply_done = {}
     step_no = [0]
     if use_peer:
         handles = [None] * world
-        dist.all_gather_object(handles, alloc.peer_export())
+        if world > 1:
+            dist.all_gather_object(handles, alloc.peer_export())
+        else:
+            handles = [alloc.peer_export()]
         alloc.peer_attach(rank, world, handles)
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
 
     def step(i):
         c, m, idx, dl, to = ring[i % nb]
-        if world == 1:
+        if world == 1 and not use_peer:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), to.data_ptr(), False, sh,
                               inputs_ready=True)
         elif use_peer:
