@@ -45,7 +45,9 @@ UNIT = "decisions/s"
 APPLY_BATCH = int(os.environ.get("EGPU_BENCH_APPLY_BATCH", "8"))   # N > 1: one apply launch covers this many steps' demand vectors
 THROTTLE = int(os.environ.get("EGPU_BENCH_THROTTLE", "16"))       # N > 1: every THROTTLE steps the scans wait for the applies of
                                                                   # two blocks ago (<= 32 steps ahead; must stay <= 16 for 64 slots)
-RING = 16  # batches in the rotation: 16 x 12 MB (1M rows) = 192 MB > 126 MB L2
+LAG = 4           # N > 1, fused apply: the scan of step k also applies step k - LAG
+RING = 32  # batches in the rotation: 32 x 12 MB (1M rows) = 384 MB > 126 MB L2; longer than a launch group (16),
+           # so that group boundaries never write where a launch still in flight writes
 
 
 def peaks():
@@ -189,8 +191,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: demand vectors through peer memory fused into the scan (default) or NCCL all-gather")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-lag", "nccl"],
+                    help="N > 1: demand vectors pushed to peer memory by the scan and applied by apply launches on a second "
+                         "stream (peer, default: measured fastest) or by a later scan's last CTA (peer-lag); or NCCL all-gather")
     ap.add_argument("--force-peer", action="store_true",
                     help="experiment: use the peer-exchange step structure even at N = 1 (exchange with self)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
@@ -253,7 +256,8 @@ def main():
     torch.cuda.synchronize()
 
     # N > 1, default: exchange fused into the scan through peer memory (CUDA IPC over NVLink)
-    use_peer = (world > 1 and args.exchange == "peer") or args.force_peer
+    use_peer = (world > 1 and args.exchange in ("peer", "peer-lag")) or args.force_peer
+    use_lag = use_peer and args.exchange == "peer-lag"
     apply_stream = torch.cuda.Stream() if use_peer else None
     apply_done = {}
     step_no = [0]
@@ -272,6 +276,13 @@ def main():
         if world == 1 and not use_peer:
             alloc.bestfit_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), to.data_ptr(), False, sh,
                               inputs_ready=True)
+        elif use_lag:
+            # one stream of scans; the last CTA of step k pushes its vector and applies step k - LAG
+            k = step_no[0]
+            step_no[0] += 1
+            lagged = ring[(i - LAG) % nb][4].data_ptr() if k >= LAG else 0
+            alloc.bestfit_shard_lag_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, LAG, lagged, sh,
+                                        inputs_ready=True)
         elif use_peer:
             # scans stay back to back on the launching stream (they overlap each other); the
             # apply kernels run on a second stream and are ordered by DATA: each waits for the
@@ -303,9 +314,18 @@ def main():
     if rank == 0:
         sampler.start()
 
+    def flush_lag():
+        """apply the last LAG steps of an eager fused-apply sequence (and consume their flags)"""
+        k1 = step_no[0]
+        first = max(0, k1 - LAG)
+        if k1 > first:
+            alloc.apply_peers_multi_dev(first, [0] * (k1 - first), False, sh)
+
     for i in range(args.warmup):
         step(i)
-    torch.cuda.synchronize()
+    if use_lag:
+        flush_lag()
+    barrier()
 
     use_graph = (world == 1 or use_peer) and not args.no_graph
     graph = None
@@ -316,7 +336,15 @@ def main():
         with torch.cuda.stream(cap):
             csh = cap.cuda_stream
             with torch.cuda.graph(graph, stream=cap):
-                if use_peer:
+                if use_lag:
+                    for k in range(args.steps):
+                        c, m, idx, dl, to = ring[k % nb]
+                        lagged = ring[(k - LAG) % nb][4].data_ptr() if k >= LAG else 0
+                        alloc.bestfit_shard_lag_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), k, LAG, lagged, csh,
+                                                    inputs_ready=True)
+                    first = max(0, args.steps - LAG)
+                    alloc.apply_peers_multi_dev(first, [ring[j % nb][4].data_ptr() for j in range(first, args.steps)], False, csh)
+                elif use_peer:
                     # two chains in the graph: scans (programmatic edges between them) and
                     # apply kernels, coupled every THROTTLE steps; step numbers restart at 0 on
                     # every replay (the apply kernel consumes the flags, so that is safe)
@@ -357,7 +385,9 @@ def main():
     else:
         for i in range(args.steps):
             step(i)
-    if use_peer and graph is None:
+    if use_lag and graph is None:  # flush the last LAG steps of the eager sequence
+        flush_lag()
+    if use_peer and not use_lag and graph is None:
         stream.wait_stream(apply_stream)  # the timed region ends when the last table' is written
     ev1.record(stream)
     barrier()
@@ -374,7 +404,7 @@ def main():
     torch.cuda.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - tw)
     launches = (alloc.launch_count - launches0) if graph is None else (
-        args.steps + (args.steps + APPLY_BATCH - 1) // APPLY_BATCH if use_peer else args.steps)
+        args.steps + 1 if use_lag else args.steps + (args.steps + APPLY_BATCH - 1) // APPLY_BATCH if use_peer else args.steps)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -610,8 +640,10 @@ def main():
                        "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
                        "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
                              if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
-                       "launch": ("CUDA graph: K scan launches whose last CTA pushes the demand vector to every peer's memory + "
-                                  "one apply launch per 8 steps on a second stream (no NCCL on the data path)") if (graph is not None and use_peer)
+                       "launch": ("CUDA graph: K scan launches; the last CTA of each pushes its demand vector to every peer's memory "
+                                  "and applies the vectors of 4 steps earlier (no NCCL, no second stream)") if (graph is not None and use_lag)
+                                 else ("CUDA graph: K scan launches whose last CTA pushes the demand vector to every peer's memory + "
+                                       "one apply launch per 8 steps on a second stream (no NCCL on the data path)") if (graph is not None and use_peer)
                                  else "CUDA graph of K scan launches" if graph is not None else
                                  ("eager launches; demand vectors pushed to peer memory by the scan's last CTA, apply kernels on a second stream"
                                   if use_peer else "eager launches + NCCL all-gather of demand vectors"),

@@ -216,6 +216,14 @@ class BestFitAllocator:
                                                     _stream(stream))
         self._check(rc, "egpu_bestfit_batch_shard_dev")
 
+    def bestfit_shard_lag_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, step: int, lag: int,
+                              d_table_out_lagged: int = 0, stream: int | None = None, inputs_ready: bool = False):
+        rc = self._lib.egpu_bestfit_batch_shard_lag_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
+                                                        C.c_void_p(d_idx), C.c_void_p(d_delta or None),
+                                                        L.F_INPUTS_READY if inputs_ready else 0, int(step), int(lag),
+                                                        C.c_void_p(d_table_out_lagged or None), _stream(stream))
+        self._check(rc, "egpu_bestfit_batch_shard_lag_dev")
+
     def apply_peers_dev(self, step: int, d_table_out: int = 0, commit: bool = False, stream: int | None = None):
         rc = self._lib.egpu_table_apply_peers_dev(self._h, int(step), C.c_void_p(d_table_out or None),
                                                   1 if commit else 0, _stream(stream))

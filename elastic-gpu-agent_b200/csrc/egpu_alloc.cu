@@ -75,7 +75,8 @@ void fill_sorted(DevState& h) {
 // chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
                     long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
-                    int rpt_hint = 0, unsigned long long push_step_plus1 = 0, bool contig = false, int* n_tiles_out = nullptr) {
+                    int rpt_hint = 0, unsigned long long push_step_plus1 = 0, bool contig = false, int* n_tiles_out = nullptr,
+                    int lag = 0) {
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
@@ -161,7 +162,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // and ordinary kernels enqueued after a PDL launch still wait for its completion.)
     if (user_flags & EGPU_F_INPUTS_READY) flags |= kFlagEarlyTrigger;
     const unsigned long long slot = (finalize ? (ctx->seq % kEpiSlots) : static_cast<unsigned long long>(kEpiSlots)) |
-                                    (push_step_plus1 << 8);
+                                    (push_step_plus1 << 8) | (static_cast<unsigned long long>(lag) << 56);
 
     // Grid: one resident wave at most.  A lone launch wants every SM pulling at once
     // (8 rows per thread, one trip); launches of a pipelined stream overlap each
@@ -632,6 +633,21 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core, const
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta), nullptr,
                            flags, true, s, 0, step + 1);
+}
+
+int egpu_bestfit_batch_shard_lag_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
+                                     int32_t* d_out_idx, int64_t* d_delta, int flags, uint64_t step, int lag,
+                                     int32_t* d_table_out_lagged, void* stream) {
+    if (!ctx || R < 0 || (flags & EGPU_F_COMMIT) || lag < 1 || lag > 16 || step >= (1ull << 47)) return EGPU_ERR_INVALID;
+    if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (!ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta), d_table_out_lagged,
+                           flags, true, s, 0, step + 1, false, nullptr, lag);
 }
 
 int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nsteps, int32_t* const* d_table_outs,

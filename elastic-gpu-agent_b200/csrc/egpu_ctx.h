@@ -65,7 +65,7 @@ struct egpu_ctx {
     uint64_t seq = 0;                 // scans launched (epilogue slot = seq mod kEpiSlots)
     int group_len = 0;                // launches since (and including) the last fully ordered one
     struct Range { uintptr_t lo, hi; } group_out[3 * kPipeGroupMax];  // their output ranges
-    int pipe_group = 16;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
+    int pipe_group = 24;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     int packed_ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the packed-format scan per D bucket, 0 = not asked yet

@@ -125,7 +125,10 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
     // slot_step: bits 0..7 = epilogue slot of this launch; bits 8.. = step + 1 when the demand
     // vector must also be pushed to the peers' exchange buffers (0 = single GPU)
     DevState::EpiSlot& ep = st->epi[slot_step & 0xffu];
-    const unsigned long long push = slot_step >> 8;
+    const unsigned long long push = (slot_step >> 8) & ((1ull << 48) - 1);
+    // bits 56..63: with push, also apply the exchanged vectors of step (step - lag) here and
+    // write ITS table' to table_out: no separate apply launches, no second stream
+    const unsigned long long lag = slot_step >> 56;
     const int tid = threadIdx.x;
     if (tid < 2 * D) {
         const int j = tid < D ? core_off + tid : mem_off + (tid - D);
@@ -170,7 +173,7 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
             }
             __threadfence_system();
         }
-        if (table_out) {
+        if (table_out && !lag) {
             table_out[tid] = sat_i32(nc);
             table_out[D + tid] = sat_i32(nm);
             table_out[2 * D + tid] = over;
@@ -194,6 +197,49 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         if (tid < world) {
             unsigned long long* f = &st->peer.buf[tid]->slot[(push - 1) % kXchgSlots][me].flag;
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(push) : "memory");
+        }
+        if (lag && push > lag) {
+            // Lagged apply, fused: the vectors of step (step - lag) have had `lag` launches to
+            // arrive, so this spin normally falls through.  It is also the back-pressure that
+            // keeps every rank within `lag` steps of the slowest one (and so inside the slots).
+            const unsigned long long ap = push - lag;  // (step - lag) + 1
+            XchgRow* rows = st->peer.buf[me]->slot[(ap - 1) % kXchgSlots];
+            if (tid == 0) *sLast = 1;
+            __syncthreads();
+            if (tid < world) {
+                unsigned long long f = 0;
+                const long long t0 = clock64();
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[tid].flag) : "memory");
+                    if (f == ap) break;
+                    if (clock64() - t0 > 4000000000ll) {
+                        *sLast = 0;
+                        break;
+                    }
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+            if (!*sLast) {
+                if (tid == 0) st->peer_timeout = ap;
+            } else {
+                long long dc = 0, dm = 0;
+                if (tid < D) {
+                    for (int g = 0; g < world; ++g) {
+                        dc += rows[g].delta[tid];
+                        dm += rows[g].delta[D + tid];
+                    }
+                }
+                __syncthreads();
+                if (tid < world) rows[tid].flag = 0ull;  // consumed (a replayed graph reuses step numbers)
+                if (tid < D && table_out) {
+                    const long long nc = static_cast<long long>(st->free_core[tid]) - dc;
+                    const long long nm = static_cast<long long>(st->free_mem[tid]) - dm;
+                    table_out[tid] = sat_i32(nc);
+                    table_out[D + tid] = sat_i32(nm);
+                    table_out[2 * D + tid] = (nc < 0 || nm < 0) ? 1 : 0;
+                }
+            }
         }
     }
     if (tid == 0) ep.ticket = 0u;

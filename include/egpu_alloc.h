@@ -208,6 +208,19 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                                  uint64_t step, void* stream);
 int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out,
                                int commit, void* stream);
+/* Scan + lagged apply in ONE launch: as egpu_bestfit_batch_shard_dev, and the same last CTA
+ * also applies the exchanged vectors of step (step - lag) (1 <= lag <= 16) and writes that
+ * step's table' to d_table_out_lagged (skipped while step < lag).  A whole sharded sequence
+ * is then a single stream of scan launches, finished by one
+ * egpu_table_apply_peers_multi_dev(first_step = last - lag + 1, lag steps) for the tail.
+ * The wait for step - lag is the back-pressure: no rank gets more than `lag` steps ahead
+ * of the slowest.  A sequence restarted from step 0 (a replayed CUDA graph) must be
+ * separated from the previous one by a barrier across the ranks.  Never commits. */
+int egpu_bestfit_batch_shard_lag_dev(egpu_ctx* ctx, const int32_t* d_req_core,
+                                     const int32_t* d_req_mem, int64_t R,
+                                     int32_t* d_out_idx, int64_t* d_delta, int flags,
+                                     uint64_t step, int lag, int32_t* d_table_out_lagged,
+                                     void* stream);
 /* Same for nsteps (1..8) consecutive steps in one launch; d_table_outs is a HOST array of
  * nsteps device pointers (entries may be NULL).  With commit the steps are applied on top
  * of each other and the last table' is installed. */

@@ -43,6 +43,40 @@ def test_world1_shard_step_equals_snapshot(alloc, oracle_c, egpu):
     alloc.peer_detach()
 
 
+def test_world1_fused_lagged_apply(alloc, oracle_c, egpu):
+    """egpu_bestfit_batch_shard_lag_dev: the scan of step k also applies step k - lag; the tail
+    is flushed by one apply launch.  More steps than exchange slots, world = 1."""
+    import torch
+    w = egpu.synth.workload("cfg3")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    alloc.peer_attach(0, 1, [alloc.peer_export()])
+    st = torch.cuda.Stream()
+    D, R, LAG, N = 8, 30_001, 3, 150
+    with torch.cuda.stream(st):
+        bufs = []
+        for step in range(N):
+            rc, rm = egpu.synth.requests(3, 500 + step, R)
+            bufs.append((rc, rm, torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda(),
+                         torch.empty(R, dtype=torch.int32, device="cuda"), torch.zeros(2 * D, dtype=torch.int64, device="cuda"),
+                         torch.full((3 * D,), -7, dtype=torch.int32, device="cuda")))
+    torch.cuda.synchronize()
+    for step in range(N):
+        _, _, c, m, idx, dl, _ = bufs[step]
+        lagged = bufs[step - LAG][6].data_ptr() if step >= LAG else 0
+        alloc.bestfit_shard_lag_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, LAG, lagged, st.cuda_stream,
+                                    inputs_ready=True)
+    alloc.apply_peers_multi_dev(N - LAG, [bufs[j][6].data_ptr() for j in range(N - LAG, N)], False, st.cuda_stream)
+    torch.cuda.synchronize()
+    assert alloc.peer_last_timeout == 0
+    for step in range(N):
+        rc, rm, _, _, idx, dl, tab = bufs[step]
+        o_idx, o_dc, o_dm, o_tab = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm, 4)
+        assert np.array_equal(idx.cpu().numpy(), o_idx), step
+        assert np.array_equal(dl.cpu().numpy(), np.concatenate([o_dc, o_dm])), step
+        assert np.array_equal(tab.cpu().numpy(), o_tab), step
+    alloc.peer_detach()
+
+
 def test_shard_calls_need_attach(alloc, egpu):
     alloc.set_table([1], [1])
     with pytest.raises(egpu.EgpuError) as ei:
@@ -50,7 +84,7 @@ def test_shard_calls_need_attach(alloc, egpu):
     assert ei.value.code == -6
 
 
-def _rank_main(rank, world, conn, peer_conn, steps, R):
+def _rank_main(rank, world, conn, peer_conn, steps, R, lag=0):
     sys.path.insert(0, ROOT)
     import torch
     import elastic_gpu_agent_b200 as e
@@ -75,9 +109,15 @@ def _rank_main(rank, world, conn, peer_conn, steps, R):
         idx = torch.empty(R, dtype=torch.int32, device="cuda")
         dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
         tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
-        a.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, s)
-        a.apply_peers_dev(step, tab.data_ptr(), step % 3 == 2, s)
+        if lag:
+            lagged = keep[step - lag][4].data_ptr() if step >= lag else 0
+            a.bestfit_shard_lag_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, lag, lagged, s)
+        else:
+            a.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, s)
+            a.apply_peers_dev(step, tab.data_ptr(), step % 3 == 2, s)
         keep.append((c, m, idx, dl, tab))
+    if lag:
+        a.apply_peers_multi_dev(steps - lag, [keep[j][4].data_ptr() for j in range(steps - lag, steps)], False, s)
     torch.cuda.synchronize()
     for c, m, idx, dl, tab in keep:
         out.append((idx.cpu().numpy(), dl.cpu().numpy(), tab.cpu().numpy()))
@@ -89,15 +129,16 @@ def _rank_main(rank, world, conn, peer_conn, steps, R):
     a.close()
 
 
-def test_world2_two_processes_one_gpu(oracle_c, egpu):
+@pytest.mark.parametrize("lag", [0, 2])
+def test_world2_two_processes_one_gpu(lag, oracle_c, egpu):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     steps, R, world, D = 7, 20_001, 2, 8
     a_conn, b_conn = ctx.Pipe()          # rank0 <-> rank1
     res0_r, res0_w = ctx.Pipe(False)
     res1_r, res1_w = ctx.Pipe(False)
-    p0 = ctx.Process(target=_rank_main, args=(0, world, res0_w, a_conn, steps, R))
-    p1 = ctx.Process(target=_rank_main, args=(1, world, res1_w, b_conn, steps, R))
+    p0 = ctx.Process(target=_rank_main, args=(0, world, res0_w, a_conn, steps, R, lag))
+    p1 = ctx.Process(target=_rank_main, args=(1, world, res1_w, b_conn, steps, R, lag))
     p0.start()
     p1.start()
     assert res0_r.poll(180) and res1_r.poll(180), "ranks did not finish"
@@ -120,7 +161,7 @@ def test_world2_two_processes_one_gpu(oracle_c, egpu):
         from elastic_gpu_agent_b200 import sharding
         etab = sharding.combine_demands(cur_c, cur_m, tot[None, :])
         assert np.array_equal(r0[1][step][2], etab) and np.array_equal(r1[1][step][2], etab)
-        if step % 3 == 2:
+        if step % 3 == 2 and not lag:  # the fused lagged apply never commits
             cur_c, cur_m = np.maximum(etab[:D], 0), np.maximum(etab[D:2 * D], 0)
     for res in (r0, r1):
         assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
