@@ -171,7 +171,8 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
                 row.delta[tid] = dc;
                 row.delta[D + tid] = dm;
             }
-            __threadfence_system();
+            // no fence here: the barrier below orders these stores before the flag stores of
+            // other threads, and st.release.sys is cumulative over what its thread has observed
         }
         if (table_out && !lag) {
             table_out[tid] = sat_i32(nc);
@@ -192,7 +193,7 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
     }
     if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
     if (push) {
-        __syncthreads();  // every delta store above is fenced; now raise the flags
+        __syncthreads();  // delta stores happen-before the release stores below
         const int world = st->peer.world, me = st->peer.rank;
         if (tid < world) {
             unsigned long long* f = &st->peer.buf[tid]->slot[(push - 1) % kXchgSlots][me].flag;
