@@ -105,6 +105,8 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
             l = pick_launch(ctx->D, grid_variant);
+            if (!grid_variant && !contig && bucket == 0 && ctx->threads8 != 256)  // experiment knob: CTA size of the D <= 8 scan
+                l = ctx->threads8 == 128 ? make_launch<8, 128>(false) : make_launch<8, 512>(false);
             if (contig) {
                 l.fn = bucket == 0 ? bestfit_sorted_kernel<8, 256, true> : bucket == 1 ? bestfit_sorted_kernel<16, 256, true>
                        : bucket == 2 ? bestfit_sorted_kernel<32, 256, true> : bestfit_sorted_kernel<64, 128, true>;
@@ -367,6 +369,10 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
         if (const char* e = std::getenv("EGPU_REPLAY_GENERAL")) ctx->replay_general = std::atoi(e) != 0;
+        if (const char* e = std::getenv("EGPU_THREADS8")) {
+            const int v = std::atoi(e);
+            ctx->threads8 = (v == 128 || v == 512) ? v : 256;
+        }
         if (const char* e = std::getenv("EGPU_LUT_THREADS")) ctx->lut_threads = std::atoi(e) == 128 ? 128 : 256;
         if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
             const int v = std::atoi(e);

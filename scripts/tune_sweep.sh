@@ -6,6 +6,6 @@ try:
 except Exception as ex: print(sys.argv[1], "FAILED", ex, open("gpurun_out/b.err").read()[-500:])
 PY
 }
-for v in 2 4; do for t in 32 48 64 96; do run EGPU_VEC=$v EGPU_ROWS_PER_THREAD=$t; done; done
-run EGPU_VEC=4 EGPU_ROWS_PER_THREAD=64 EGPU_PIPE_GROUP=24
-run EGPU_VEC=2 EGPU_ROWS_PER_THREAD=48 EGPU_PIPE_GROUP=24
+run EGPU_THREADS8=256
+for t in 24 48 96; do run EGPU_THREADS8=128 EGPU_ROWS_PER_THREAD=$t; done
+for t in 24 48 96; do run EGPU_THREADS8=512 EGPU_ROWS_PER_THREAD=$t; done
