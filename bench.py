@@ -416,7 +416,7 @@ def main():
     if rank == 0 and world == 1 and R <= (1 << 20):
         from oracle import oracle_c
         parity = True
-        for b in range(nb):
+        for b in range(min(nb, args.steps)):  # the ring entries the timed steps actually wrote
             rc_h, rm_h = e.synth.requests(w["dist"], w["seed"], R, first_row=(rank * nb + b) * R)
             exp, edc, edm, etab = oracle_c.snapshot(w["free_core"], w["free_mem"], rc_h, rm_h, oracle_c.max_threads())
             parity = parity and bool(np.array_equal(ring[b][2].cpu().numpy(), exp))
@@ -426,7 +426,7 @@ def main():
     if rank == 0 and use_peer and R <= (1 << 20):
         from oracle import oracle_c
         parity = alloc.peer_last_timeout == 0
-        for b in range(min(nb, 4)):
+        for b in range(min(nb, 4, args.steps)):
             tot_c = np.zeros(D, dtype=np.int64)
             tot_m = np.zeros(D, dtype=np.int64)
             for g in range(world):
