@@ -278,7 +278,8 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
 // CONTIG = true (prefix-commit mode): CTA b scans the contiguous rows of "tile" b and leaves
 // its per-device sums in tile_sums[b][*]; everything else is the same kernel.
 template <int DT, int THREADS, bool CONTIG = false>
-__global__ void __launch_bounds__(THREADS, (DT == 8 && THREADS == 256) ? 5 : 1)  // D <= 8: keep 5 CTAs (40 warps) per SM
+__global__ void __launch_bounds__(THREADS)  // (forcing 5 CTAs/SM = 48 registers was measured slower: ptxas then puts
+                                            //  more of the adds on the ALU pipe; same-box A/B)
 bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                       const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
                       long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
