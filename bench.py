@@ -612,6 +612,29 @@ def main():
             "note": "types.NewDevice + hash over every candidate container, as KubeletDeviceLocator.Locate does per container start; "
                     "C-ABI calls only (host buffers in, hashes out: H2D, sort, render, SHA-256, D2H); CPU port = qsort + SHA-256 in C, one thread"}
 
+        # restore: the same 96 containers as stored records + symlinks -> free table (row n3)
+        from elastic_gpu_agent_b200 import restore
+        from oracle import restore_py
+        recs, lnk = [], []
+        for c, x in enumerate(sets):
+            recs.append(restore_py.marshal_record("default", "pod-%d" % c, {"main": (x, restore_py.MEM)}))
+            lnk.append(("elastic-gpu-%s-0" % ref[c], "/dev/nvidia%d" % (c % 8)))
+        capc, capm = [100] * 8, [183359] * 8
+        restore.restore_table(alloc, recs[:2], lnk, capc, capm)  # warm-up
+        t0 = time.perf_counter()
+        rfc, rfm, rov, rcounts, _ = restore.restore_table(alloc, recs, lnk, capc, capm)
+        dt_r = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ofc, ofm, oov, ocounts, _ = restore_py.restore(recs, lnk, capc, capm)
+        dt_ro = time.perf_counter() - t0
+        extra["placement_restore"] = {
+            "records": len(recs), "ids": n_ids, "record_bytes": sum(len(v) for _, v in recs),
+            "gpu_ms_e2e": 1e3 * dt_r, "cpu_restatement_ms": 1e3 * dt_ro,
+            "equal_to_oracle": bool(rfc.tolist() == ofc and rfm.tolist() == ofm and rov.tolist() == oov
+                                    and rcounts.tolist() == ocounts and int(rcounts[0]) == len(recs)),
+            "note": "egpu_table_restore on the raw Bolt values (JSON parse on the host, identity check + usage sums on the "
+                    "GPU); the CPU side is the Python restatement (json + sorted + hashlib), one thread"}
+
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------
     cpu = None
     if rank == 0 and world == 1:

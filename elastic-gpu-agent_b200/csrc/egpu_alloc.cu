@@ -453,6 +453,21 @@ int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_
         if (free_mem[d] < 0 || free_mem[d] > EGPU_MEM_MAX) return EGPU_ERR_INVALID;
     }
     std::lock_guard<std::mutex> g(ctx->mu);
+    return egpu_table_set_locked(ctx, free_core, free_mem, D);
+}
+
+}  // extern "C"
+
+// for the host-only translation units (egpu_restore.cc), which cannot see egpu_ctx
+void egpu_note_error(egpu_ctx* ctx, const char* msg) {
+    if (!ctx || !msg) return;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    std::snprintf(ctx->last_err, sizeof ctx->last_err, "%s", msg);
+}
+
+// body of egpu_table_set; the caller holds ctx->mu and has validated the arguments
+// (also used by egpu_table_restore_flat, egpu_devhash.cu)
+int egpu_table_set_locked(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D) {
     EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
     DevState h;
     std::memset(&h, 0, sizeof h);
@@ -472,6 +487,8 @@ int egpu_table_set(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_
     ctx->lut_dirty = true;
     return EGPU_OK;
 }
+
+extern "C" {
 
 int egpu_table_size(egpu_ctx* ctx) {
     if (!ctx) return EGPU_ERR_INVALID;

@@ -85,6 +85,9 @@ inline int cuda_fail(egpu_ctx* ctx, cudaError_t e, const char* what) {
     return e == cudaErrorMemoryAllocation ? EGPU_ERR_NOMEM : EGPU_ERR_CUDA;
 }
 
+// egpu_alloc.cu: body of egpu_table_set for callers that already hold ctx->mu
+int egpu_table_set_locked(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D);
+
 #define EGPU_CUDA(ctx, call)                                   \
     do {                                                       \
         cudaError_t e__ = (call);                              \

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/egpu_devhash.h"
+#include "../../include/egpu_restore.h"
 #include "egpu_ctx.h"
 
 namespace egpu {
@@ -600,3 +601,153 @@ int egpu_device_locate(egpu_ctx* ctx, const char* ids_flat, const int64_t* id_of
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Placement-state restore (include/egpu_restore.h)
+// ---------------------------------------------------------------------------------------------
+namespace egpu {
+
+constexpr int kResBadHash = -2;  // host-side marker: the stored Hash is not 8 hex digits
+
+// One thread per stored entry: check the stored Hash against the recomputed identity, resolve
+// its symlinks, add what it holds to the per-GPU usage sums (int64: 64 x 2^18 MiB fits easily,
+// but so does any corrupt input).
+__global__ void restore_usage_kernel(const long long* __restrict__ set_off, long long n_sets,
+                                     const uint32_t* __restrict__ digest /* [n_sets][8] or nullptr */,
+                                     const uint32_t* __restrict__ stored_hash, const int32_t* __restrict__ resource,
+                                     const long long* __restrict__ link_off, const int32_t* __restrict__ link_gpu,
+                                     int D, unsigned long long* __restrict__ usage /* [2][kMaxD] */,
+                                     int32_t* __restrict__ status) {
+    const long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (s >= n_sets) return;
+    const long long n = set_off[s + 1] - set_off[s];
+    const int res = resource[s];
+    int st = EGPU_REC_OK;
+    if (res != EGPU_RESOURCE_CORE && res != EGPU_RESOURCE_MEM && res != kResBadHash) {
+        st = EGPU_REC_FOREIGN;
+    } else if (n == 0) {
+        st = EGPU_REC_EMPTY;
+    } else if (res == kResBadHash || (digest && digest[s * 8] != stored_hash[s])) {
+        st = EGPU_REC_HASH_MISMATCH;
+    } else {
+        const long long l0 = link_off[s], nl = link_off[s + 1] - l0;
+        const long long need = (res == EGPU_RESOURCE_CORE && n > 100) ? n / 100 : 1;
+        if (nl < need) st = EGPU_REC_NO_LINK;
+        for (long long i = 0; st == EGPU_REC_OK && i < need; ++i) {
+            const int g = link_gpu[l0 + i];
+            if (g < 0 || g >= D) st = EGPU_REC_NO_LINK;
+        }
+        if (st == EGPU_REC_OK) {
+            if (res == EGPU_RESOURCE_MEM) {
+                atomicAdd(&usage[kMaxD + link_gpu[l0]], static_cast<unsigned long long>(n));
+            } else if (n <= 100) {
+                atomicAdd(&usage[link_gpu[l0]], static_cast<unsigned long long>(n));
+            } else {
+                for (long long i = 0; i < need; ++i) atomicAdd(&usage[link_gpu[l0 + i]], 100ull);
+            }
+        }
+    }
+    status[s] = st;
+}
+
+// free = capacity - usage, saturated at 0, with the oversubscription flag of table'
+__global__ void __launch_bounds__(kMaxD)
+restore_table_kernel(const int32_t* __restrict__ cap /* [2][kMaxD] */, const unsigned long long* __restrict__ usage, int D,
+                     int32_t* __restrict__ table_out /* [3 * D] */) {
+    const int d = threadIdx.x;
+    if (d >= D) return;
+    const long long c = static_cast<long long>(cap[d]) - static_cast<long long>(usage[d]);
+    const long long m = static_cast<long long>(cap[kMaxD + d]) - static_cast<long long>(usage[kMaxD + d]);
+    table_out[d] = c < 0 ? 0 : static_cast<int32_t>(c);
+    table_out[D + d] = m < 0 ? 0 : static_cast<int32_t>(m);
+    table_out[2 * D + d] = (c < 0 || m < 0) ? 1 : 0;
+}
+
+}  // namespace egpu
+
+extern "C" int egpu_table_restore_flat(egpu_ctx* ctx, const char* ids_flat, const int64_t* id_offsets, int64_t n_ids,
+                                       const int64_t* set_offsets, int64_t n_sets, const char* set_hash8,
+                                       const int32_t* set_resource, const int64_t* link_offsets, const int32_t* link_gpu,
+                                       const int32_t* cap_core, const int32_t* cap_mem, int32_t D, int flags,
+                                       int32_t* out_table, int32_t* out_status) {
+    if (!ctx || !out_table || !cap_core || !cap_mem || D < 1 || D > EGPU_MAX_DEVICES || n_sets < 0 || n_ids < 0)
+        return EGPU_ERR_INVALID;
+    if (flags & ~(EGPU_RESTORE_VERIFY | EGPU_RESTORE_INSTALL)) return EGPU_ERR_INVALID;
+    for (int d = 0; d < D; ++d) {
+        if (cap_core[d] < 0 || cap_core[d] > EGPU_CORE_MAX) return EGPU_ERR_INVALID;
+        if (cap_mem[d] < 0 || cap_mem[d] > EGPU_MEM_MAX) return EGPU_ERR_INVALID;
+    }
+    const bool verify = (flags & EGPU_RESTORE_VERIFY) != 0;
+    std::vector<uint32_t> stored(static_cast<size_t>(n_sets), 0);
+    std::vector<int32_t> res(static_cast<size_t>(n_sets), 0);
+    if (n_sets > 0) {
+        if (!set_offsets || !id_offsets || !set_resource || !link_offsets || !set_hash8) return EGPU_ERR_INVALID;
+        if (link_offsets[0] != 0) return EGPU_ERR_INVALID;
+        for (int64_t q = 0; q < n_sets; ++q) {
+            if (link_offsets[q + 1] < link_offsets[q]) return EGPU_ERR_INVALID;
+            uint32_t w = 0;
+            bool ok = true;
+            for (int k = 0; k < 8; ++k) {
+                const char c = set_hash8[q * 8 + k];
+                const int v = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : -1;
+                ok = ok && v >= 0;
+                w = (w << 4) | static_cast<uint32_t>(v & 15);
+            }
+            stored[q] = w;
+            res[q] = set_resource[q];
+            // a stored Hash that is not 8 lowercase hex digits can never equal a recomputed one
+            if (!ok && verify && (res[q] == EGPU_RESOURCE_CORE || res[q] == EGPU_RESOURCE_MEM)) res[q] = kResBadHash;
+        }
+        if (link_offsets[n_sets] > 0 && !link_gpu) return EGPU_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    std::vector<int32_t> table(static_cast<size_t>(3) * D, 0);
+    std::vector<int32_t> status(static_cast<size_t>(n_sets), EGPU_REC_OK);
+    if (n_sets == 0) {
+        for (int d = 0; d < D; ++d) table[d] = cap_core[d], table[D + d] = cap_mem[d];
+    } else {
+        HashRun r;
+        // the hash pipeline carves the arena first; the restore buffers are separate small allocations
+        const int rc = run_hash(ctx, r, ids_flat, id_offsets, n_ids, set_offsets, n_sets, verify);
+        if (rc != EGPU_OK) return rc;
+        const int64_t n_links = link_offsets[n_sets];
+        struct Tmp {
+            void* p = nullptr;
+            ~Tmp() { if (p) cudaFree(p); }
+        } buf;
+        const size_t o_stored = 0, o_res = o_stored + 4 * static_cast<size_t>(n_sets), o_status = o_res + 4 * static_cast<size_t>(n_sets);
+        size_t o_loff = (o_status + 4 * static_cast<size_t>(n_sets) + 7) & ~static_cast<size_t>(7);
+        const size_t o_lgpu = o_loff + 8 * static_cast<size_t>(n_sets + 1);
+        size_t o_usage = (o_lgpu + 4 * static_cast<size_t>(n_links > 0 ? n_links : 1) + 7) & ~static_cast<size_t>(7);
+        const size_t o_cap = o_usage + 8 * 2 * kMaxD, o_table = o_cap + 4 * 2 * kMaxD, total = o_table + 4 * 3 * kMaxD;
+        EGPU_CUDA(ctx, cudaMalloc(&buf.p, total));
+        char* b = static_cast<char*>(buf.p);
+        int32_t cap[2 * kMaxD] = {0};
+        for (int d = 0; d < D; ++d) cap[d] = cap_core[d], cap[kMaxD + d] = cap_mem[d];
+        EGPU_CUDA(ctx, cudaMemcpyAsync(b + o_stored, stored.data(), 4 * n_sets, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(b + o_res, res.data(), 4 * n_sets, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(b + o_loff, link_offsets, 8 * (n_sets + 1), cudaMemcpyHostToDevice, s));
+        if (n_links) EGPU_CUDA(ctx, cudaMemcpyAsync(b + o_lgpu, link_gpu, 4 * n_links, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(b + o_cap, cap, sizeof cap, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemsetAsync(b + o_usage, 0, 8 * 2 * kMaxD, s));
+        restore_usage_kernel<<<static_cast<unsigned>((n_sets + 127) / 128), 128, 0, s>>>(
+            r.set_off.as<long long>(), n_sets, verify ? r.digest.as<uint32_t>() : nullptr,
+            reinterpret_cast<const uint32_t*>(b + o_stored), reinterpret_cast<const int32_t*>(b + o_res),
+            reinterpret_cast<const long long*>(b + o_loff), reinterpret_cast<const int32_t*>(b + o_lgpu), D,
+            reinterpret_cast<unsigned long long*>(b + o_usage), reinterpret_cast<int32_t*>(b + o_status));
+        restore_table_kernel<<<1, kMaxD, 0, s>>>(reinterpret_cast<const int32_t*>(b + o_cap),
+                                                 reinterpret_cast<const unsigned long long*>(b + o_usage), D,
+                                                 reinterpret_cast<int32_t*>(b + o_table));
+        ctx->launches += 2;
+        EGPU_CUDA(ctx, cudaGetLastError());
+        EGPU_CUDA(ctx, cudaMemcpyAsync(status.data(), b + o_status, 4 * n_sets, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(table.data(), b + o_table, 4 * 3 * static_cast<size_t>(D), cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    std::memcpy(out_table, table.data(), sizeof(int32_t) * 3 * static_cast<size_t>(D));
+    if (out_status && n_sets) std::memcpy(out_status, status.data(), sizeof(int32_t) * static_cast<size_t>(n_sets));
+    if (flags & EGPU_RESTORE_INSTALL) return egpu_table_set_locked(ctx, table.data(), table.data() + D, D);
+    return EGPU_OK;
+}

@@ -76,7 +76,7 @@ extern "C" {
 #define EGPU_ERR_NOMEM       (-4)   /* host or device allocation failed */
 #define EGPU_ERR_NO_TABLE    (-5)   /* egpu_table_set has not been called */
 #define EGPU_ERR_STATE       (-6)   /* call not valid in the current state */
-#define EGPU_ERR_PARSE       (-7)   /* malformed device-ID string */
+#define EGPU_ERR_PARSE       (-7)   /* malformed device-ID string or stored record */
 #define EGPU_ERR_UNSAT       (-8)   /* preferred allocation cannot be satisfied */
 
 /* event kinds for egpu_replay */
