@@ -87,6 +87,7 @@ def load() -> C.CDLL:
         "egpu_peer_attach": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "egpu_peer_detach": (C.c_int, [vp]),
         "egpu_bestfit_batch_shard_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, C.c_int, C.c_uint64, vp]),
+        "egpu_bestfit_batch_shard_prefix_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int, C.c_uint64, vp]),
         "egpu_bestfit_batch_shard_lag_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, C.c_int, C.c_uint64, C.c_int, vp, vp]),
         "egpu_table_apply_peers_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),
         "egpu_table_apply_peers_multi_dev": (C.c_int, [vp, C.c_uint64, C.c_int, vp, C.c_int, vp]),

@@ -216,6 +216,16 @@ class BestFitAllocator:
                                                     _stream(stream))
         self._check(rc, "egpu_bestfit_batch_shard_dev")
 
+    def bestfit_shard_prefix_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, d_table_out: int, step: int,
+                                 commit: bool = False, stream: int | None = None):
+        """Prefix-commit over row shards (rank-major order); consumes exchange steps `step` and `step + 1`."""
+        rc = self._lib.egpu_bestfit_batch_shard_prefix_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),
+                                                           C.c_void_p(d_idx), C.c_void_p(d_delta or None),
+                                                           C.c_void_p(d_table_out or None),
+                                                           L.F_PREFIX_COMMIT | (L.F_COMMIT if commit else 0), int(step),
+                                                           _stream(stream))
+        self._check(rc, "egpu_bestfit_batch_shard_prefix_dev")
+
     def bestfit_shard_lag_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, d_delta: int, step: int, lag: int,
                               d_table_out_lagged: int = 0, stream: int | None = None, inputs_ready: bool = False):
         rc = self._lib.egpu_bestfit_batch_shard_lag_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R),

@@ -232,7 +232,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
 // rewrite of the deferred indices -> delta / table' of the committed rows only.
 int launch_prefix_commit(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
                          long long* d_delta, int32_t* d_table_out, int user_flags, cudaStream_t s) {
-    if (!ctx->d_prefix_out) EGPU_CUDA(ctx, cudaMalloc(&ctx->d_prefix_out, sizeof(PrefixOut)));
+    if (!ctx->d_prefix_out) EGPU_CUDA(ctx, cudaMalloc(&ctx->d_prefix_out, sizeof(PrefixOut) + sizeof(long long) * 2 * kMaxD));
     int n_tiles = 0;
     // the scan itself must neither publish nor commit: its sums are the uncapped ones
     int rc = launch_snapshot(ctx, d_rc, d_rm, R, d_idx, nullptr, nullptr, 0, true, s, 0, 0, true, &n_tiles);
@@ -247,6 +247,36 @@ int launch_prefix_commit(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm
     prefix_finalize_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, pf, d_delta, d_table_out, (user_flags & EGPU_F_COMMIT) ? 1 : 0);
     EGPU_CUDA(ctx, cudaGetLastError());
     ctx->launches += 3;
+    ctx->prev_is_scan = false;
+    if (user_flags & EGPU_F_COMMIT) ctx->lut_dirty = true;
+    return EGPU_OK;
+}
+
+// Prefix-commit over row shards (one rank per GPU, rank-major row order).  Two exchange
+// steps: `step` carries the uncapped demand of every shard (pushed by the scan itself),
+// `step + 1` the committed demand after the cut (pushed by prefix_push_kernel).
+int launch_prefix_commit_shard(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
+                               long long* d_delta, int32_t* d_table_out, int user_flags, uint64_t step, cudaStream_t s) {
+    if (!ctx->d_prefix_out) EGPU_CUDA(ctx, cudaMalloc(&ctx->d_prefix_out, sizeof(PrefixOut) + sizeof(long long) * 2 * kMaxD));
+    PrefixOut* pf = static_cast<PrefixOut*>(ctx->d_prefix_out);
+    long long* base = reinterpret_cast<long long*>(pf + 1);
+    int n_tiles = 0;
+    // finalising scan without commit: its epilogue publishes (and pushes) the uncapped sums
+    int rc = launch_snapshot(ctx, d_rc, d_rm, R, d_idx, nullptr, nullptr, 0, true, s, 0, step + 1, true, &n_tiles);
+    if (rc != EGPU_OK) return rc;
+    prefix_base_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, step + 1, base);
+    prefix_cut_kernel<<<ctx->D, 256, 0, s>>>(ctx->d_state, d_idx, d_rc, d_rm, R, n_tiles, ctx->d_tile_sums, pf, base);
+    int64_t blocks = (R + 1023) / 1024;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    prefix_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pf, ctx->D, R, d_idx);
+    prefix_push_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, pf, step + 2, d_delta);
+    ApplyOuts outs{};
+    outs.table_out[0] = d_table_out;
+    apply_peers_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, step + 2, 1, outs, (user_flags & EGPU_F_COMMIT) ? 1 : 0);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 5;
     ctx->prev_is_scan = false;
     if (user_flags & EGPU_F_COMMIT) ctx->lut_dirty = true;
     return EGPU_OK;
@@ -656,6 +686,21 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core, const
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta), nullptr,
                            flags, true, s, 0, step + 1);
+}
+
+int egpu_bestfit_batch_shard_prefix_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
+                                        int32_t* d_out_idx, int64_t* d_delta, int32_t* d_table_out, int flags,
+                                        uint64_t step, void* stream) {
+    if (!ctx || R < 0 || step >= (1ull << 47) || (flags & ~(EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT))) return EGPU_ERR_INVALID;
+    if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (!ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_prefix_commit_shard(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta),
+                                      d_table_out, flags, step, s);
 }
 
 int egpu_bestfit_batch_shard_lag_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,

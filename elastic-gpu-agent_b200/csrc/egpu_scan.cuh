@@ -932,7 +932,8 @@ __device__ __forceinline__ void block_scan2(unsigned long long& a, unsigned long
 __global__ void __launch_bounds__(256)
 prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ idx, const int32_t* __restrict__ req_core,
                   const int32_t* __restrict__ req_mem, long long R, int n_tiles,
-                  const unsigned long long* __restrict__ tile_sums, PrefixOut* __restrict__ out) {
+                  const unsigned long long* __restrict__ tile_sums, PrefixOut* __restrict__ out,
+                  const long long* __restrict__ base = nullptr /* [2][kMaxD]: demand of the lower ranks' rows */) {
     constexpr int T = 256;
     __shared__ unsigned long long sh[2 * (T / 32)];
     __shared__ long long sCutTile, sCutRow;
@@ -941,10 +942,22 @@ prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ i
     const int tid = threadIdx.x;
     const unsigned long long cap_c = static_cast<unsigned long long>(st->free_core[d]);
     const unsigned long long cap_m = static_cast<unsigned long long>(st->free_mem[d]);
+    // Multi-GPU (rank-major row order): the rows of the lower ranks come first, so their whole
+    // demand on this device is already on the running sums when this shard starts
+    const unsigned long long pre_c = base ? static_cast<unsigned long long>(base[d]) : 0ull;
+    const unsigned long long pre_m = base ? static_cast<unsigned long long>(base[kMaxD + d]) : 0ull;
+    if (pre_c > cap_c || pre_m > cap_m) {  // the device filled up on a lower rank: nothing commits here
+        if (tid == 0) {
+            out->cut[d] = 0;
+            out->committed_c[d] = 0;
+            out->committed_m[d] = 0;
+        }
+        return;
+    }
     if (tid == 0) { sCutTile = n_tiles; sCutRow = R; sBaseC = 0; sBaseM = 0; sComC = 0; sComM = 0; }
     __syncthreads();
     // (1) which tile crosses capacity?
-    unsigned long long run_c = 0, run_m = 0;
+    unsigned long long run_c = pre_c, run_m = pre_m;
     for (int t0 = 0; t0 < n_tiles; t0 += T) {
         const int t = t0 + tid;
         unsigned long long c = t < n_tiles ? tile_sums[static_cast<size_t>(t) * 2 * kMaxD + d] : 0ull;
@@ -966,8 +979,8 @@ prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ i
     if (cut_tile >= n_tiles) {  // the device never fills up: everything that chose it commits
         if (tid == 0) {
             out->cut[d] = R;
-            out->committed_c[d] = static_cast<long long>(run_c);
-            out->committed_m[d] = static_cast<long long>(run_m);
+            out->committed_c[d] = static_cast<long long>(run_c - pre_c);
+            out->committed_m[d] = static_cast<long long>(run_m - pre_m);
         }
         return;
     }
@@ -980,7 +993,7 @@ prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ i
         }
         unsigned long long tc, tm;
         block_scan2<T>(c, m, sh, tc, tm);
-        if (tid == 0) { sBaseC = tc; sBaseM = tm; }
+        if (tid == 0) { sBaseC = pre_c + tc; sBaseM = pre_m + tm; }
         __syncthreads();
     }
     // (2) rows of the cut tile, in order
@@ -1027,8 +1040,8 @@ prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ i
     __syncthreads();
     if (tid == 0) {
         out->cut[d] = sCutRow;
-        out->committed_c[d] = static_cast<long long>(sCutRow < R ? sComC : base_c);
-        out->committed_m[d] = static_cast<long long>(sCutRow < R ? sComM : base_m);
+        out->committed_c[d] = static_cast<long long>((sCutRow < R ? sComC : base_c) - pre_c);
+        out->committed_m[d] = static_cast<long long>((sCutRow < R ? sComM : base_m) - pre_m);
     }
 }
 
@@ -1071,6 +1084,81 @@ prefix_finalize_kernel(DevState* __restrict__ st, const PrefixOut* __restrict__ 
         }
     }
     if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, d);
+}
+
+// Prefix-commit across GPUs (spec 2.5 "rank-major across shards").  The global row order is
+// rank 0's shard, then rank 1's, ...; the scan of every rank has pushed its UNCAPPED demand
+// vector of exchange step `step` to every peer (epilogue_publish).  This kernel waits for
+// them in this rank's own buffer and leaves base[d] = demand of the ranks below this one:
+// what is already on the running sums when this shard's first row is considered.  One CTA.
+__global__ void __launch_bounds__(kMaxD)
+prefix_base_kernel(DevState* __restrict__ st, unsigned long long step_plus1, long long* __restrict__ base /* [2][kMaxD] */) {
+    __shared__ int sOk;
+    const int D = st->D;
+    const int d = threadIdx.x;
+    const int world = st->peer.world, me = st->peer.rank;
+    XchgRow* rows = st->peer.buf[me]->slot[(step_plus1 - 1) % kXchgSlots];
+    if (d == 0) sOk = 1;
+    __syncthreads();
+    if (d < world) {  // all ranks, not only the lower ones: the flags are consumed below
+        unsigned long long f = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[d].flag) : "memory");
+            if (f == step_plus1) break;
+            if (clock64() - t0 > 4000000000ll) {
+                sOk = 0;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (!sOk) {  // a rank died: defer everything here (base beyond any capacity) and record it
+        if (d == 0) st->peer_timeout = step_plus1;
+        base[d] = 1ll << 40;
+        base[kMaxD + d] = 1ll << 40;
+        return;
+    }
+    long long bc = 0, bm = 0;
+    if (d < D) {
+        for (int g = 0; g < me; ++g) {
+            bc += rows[g].delta[d];
+            bm += rows[g].delta[D + d];
+        }
+    }
+    base[d] = bc;
+    base[kMaxD + d] = bm;
+    __syncthreads();
+    if (d < world) rows[d].flag = 0ull;  // consumed (a replayed CUDA graph pushes the same step again)
+}
+
+// This rank's COMMITTED demand (after the cut) to every peer as exchange step `step`;
+// apply_peers_kernel of that step then makes table' = table - sum over ranks.  One CTA.
+__global__ void __launch_bounds__(kMaxD)
+prefix_push_kernel(DevState* __restrict__ st, const PrefixOut* __restrict__ pf, unsigned long long step_plus1,
+                   long long* __restrict__ delta_out) {
+    const int D = st->D;
+    const int d = threadIdx.x;
+    const int world = st->peer.world, me = st->peer.rank;
+    const int xs = static_cast<int>((step_plus1 - 1) % kXchgSlots);
+    if (d < D) {
+        const long long dc = pf->committed_c[d], dm = pf->committed_m[d];
+        if (delta_out) {
+            delta_out[d] = dc;
+            delta_out[D + d] = dm;
+        }
+        for (int p = 0; p < world; ++p) {
+            XchgRow& row = st->peer.buf[p]->slot[xs][me];
+            row.delta[d] = dc;
+            row.delta[D + d] = dm;
+        }
+    }
+    __syncthreads();  // the vector stores happen-before the release stores of the flags
+    if (d < world) {
+        unsigned long long* f = &st->peer.buf[d]->slot[xs][me].flag;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(step_plus1) : "memory");
+    }
 }
 
 }  // namespace egpu

@@ -65,3 +65,4 @@ def sharded_step(alloc, d_core: int, d_mem: int, rows: int, d_idx: int, delta, g
     else:
         gathered_flat.copy_(delta)
     alloc.apply_deltas_dev(gathered_flat.data_ptr(), world, table_out.data_ptr(), commit, stream)
+

@@ -208,6 +208,22 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                                  uint64_t step, void* stream);
 int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out,
                                int commit, void* stream);
+/* Prefix-commit (EGPU_F_PREFIX_COMMIT semantics, see egpu_bestfit_batch) over row shards.
+ * The batch is the concatenation of the ranks' shards in rank order; request r of rank g
+ * commits iff the running demand of its device over ALL earlier rows - the whole shards of
+ * ranks < g and the rows before r here - still fits ("rank-major
+ * across shards").  One asynchronous call per rank; it uses TWO exchange steps, `step` (the
+ * uncapped demand of every shard, pushed by the scan itself; every rank then knows the base
+ * offset of its shard) and `step + 1` (the committed demand after the cut), so the caller
+ * advances `step` by 2.  Outputs: d_out_idx with EGPU_IDX_DEFERRED for the rows beyond the
+ * cut; d_delta[2*D] = THIS rank's committed demand (may be NULL); d_table_out[3*D] =
+ * table - committed demand of all ranks, identical on every rank (may be NULL);
+ * EGPU_F_COMMIT installs it.  Never oversubscribes. */
+int egpu_bestfit_batch_shard_prefix_dev(egpu_ctx* ctx, const int32_t* d_req_core,
+                                        const int32_t* d_req_mem, int64_t R,
+                                        int32_t* d_out_idx, int64_t* d_delta,
+                                        int32_t* d_table_out, int flags, uint64_t step,
+                                        void* stream);
 /* Scan + lagged apply in ONE launch: as egpu_bestfit_batch_shard_dev, and the same last CTA
  * also applies the exchanged vectors of step (step - lag) (1 <= lag <= 16) and writes that
  * step's table' to d_table_out_lagged (skipped while step < lag).  A whole sharded sequence

@@ -165,3 +165,145 @@ def test_world2_two_processes_one_gpu(lag, oracle_c, egpu):
             cur_c, cur_m = np.maximum(etab[:D], 0), np.maximum(etab[D:2 * D], 0)
     for res in (r0, r1):
         assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
+
+
+# ------------------------------------------------------------------ prefix-commit over shards
+def _rank_partial(idx, rc, rm, D):
+    d = np.zeros(2 * D, dtype=np.int64)
+    ok = idx >= 0
+    np.add.at(d, idx[ok], rc[ok].astype(np.int64))
+    np.add.at(d, D + idx[ok], rm[ok].astype(np.int64))
+    return d
+
+
+def test_world1_shard_prefix_equals_single_gpu_prefix_commit(alloc, oracle_c, egpu):
+    """world = 1: the sharded entry point must be the plain prefix-commit (base offset 0)."""
+    import torch
+    D = 8
+    fc, fm = egpu.synth.table_full(D)
+    alloc.set_table(fc, fm)
+    alloc.peer_attach(0, 1, [alloc.peer_export()])
+    s = torch.cuda.current_stream().cuda_stream
+    cur_c, cur_m = fc.copy(), fm.copy()
+    for k, R in enumerate([37, 20_003, 1, 0, 4096]):
+        rc, rm = egpu.synth.requests(2, 300 + k, R)
+        c = torch.from_numpy(rc).cuda() if R else torch.empty(4, dtype=torch.int32, device="cuda")
+        m = torch.from_numpy(rm).cuda() if R else torch.empty(4, dtype=torch.int32, device="cuda")
+        idx = torch.empty(max(R, 4), dtype=torch.int32, device="cuda")
+        dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+        tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+        alloc.bestfit_shard_prefix_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), tab.data_ptr(), 2 * k,
+                                       commit=True, stream=s)
+        torch.cuda.synchronize()
+        o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(cur_c, cur_m, rc, rm)
+        assert np.array_equal(idx[:R].cpu().numpy(), o_idx), k
+        assert np.array_equal(dl.cpu().numpy(), np.concatenate([o_dc, o_dm])), k
+        assert np.array_equal(tab.cpu().numpy(), o_tab), k
+        cur_c, cur_m = o_tab[:D].copy(), o_tab[D:2 * D].copy()
+        if k == 1:  # start again from a roomy table so the later steps still place something
+            cur_c, cur_m = fc.copy(), fm.copy()
+            alloc.set_table(fc, fm)
+    assert alloc.peer_last_timeout == 0
+    g_c, g_m, _ = alloc.table()
+    assert np.array_equal(g_c, cur_c) and np.array_equal(g_m, cur_m)
+    alloc.peer_detach()
+
+
+PREFIX_STEPS = [(7, 20_001, True), (3, 50, True), (0, 64, True), (1_000, 1_000, True), (5, 5, False), (2, 3, True),
+                (30_000, 30_000, True)]  # (rows of rank 0, rows of rank 1, fresh table?)
+PREFIX_FC = np.array([100, 100, 70, 30, 100, 50, 100, 100], dtype=np.int32)
+PREFIX_FM = np.array([183359, 183359, 183359, 60, 183359, 183359, 183359, 183359], dtype=np.int32)
+
+
+def _prefix_requests(k, n):
+    """Four request classes that the best-fit rule sends to different devices of PREFIX_FC/FM, so
+    several devices fill up at different rows: core 1..4 and core 0 -> device 3 (30 %, 60 MiB: the
+    cut may come from either resource), core 31..34 -> device 5, core 51..54 -> device 2."""
+    rng = np.random.default_rng(1000 + k)
+    cls = rng.integers(0, 4, n)
+    core = np.select([cls == 0, cls == 1, cls == 2], [rng.integers(1, 5, n), rng.integers(31, 35, n), rng.integers(51, 55, n)], 0)
+    mem = rng.integers(1, 9, n)
+    return core.astype(np.int32), mem.astype(np.int32)
+
+
+def _prefix_rank_main(rank, world, conn, peer_conn):
+    sys.path.insert(0, ROOT)
+    import torch
+    import elastic_gpu_agent_b200 as e
+    torch.cuda.set_device(0)
+    a = e.BestFitAllocator(0)
+    a.set_table(PREFIX_FC, PREFIX_FM)
+    mine = a.peer_export()
+    peer_conn.send(mine)
+    other = peer_conn.recv()
+    a.peer_attach(rank, world, [mine, other] if rank == 0 else [other, mine])
+    peer_conn.send("attached")
+    assert peer_conn.recv() == "attached"
+    s = torch.cuda.current_stream().cuda_stream
+    D = 8
+    out = []
+    for k, (r0, r1, fresh) in enumerate(PREFIX_STEPS):
+        R = r0 if rank == 0 else r1
+        if fresh:
+            torch.cuda.synchronize()
+            a.set_table(PREFIX_FC, PREFIX_FM)
+        rc, rm = _prefix_requests(k, r0 + r1)
+        rc, rm = (rc[:r0], rm[:r0]) if rank == 0 else (rc[r0:], rm[r0:])
+        rc, rm = np.ascontiguousarray(rc), np.ascontiguousarray(rm)
+        c = torch.from_numpy(rc).cuda() if R else torch.empty(4, dtype=torch.int32, device="cuda")
+        m = torch.from_numpy(rm).cuda() if R else torch.empty(4, dtype=torch.int32, device="cuda")
+        idx = torch.empty(max(R, 4), dtype=torch.int32, device="cuda")
+        dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+        tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+        a.bestfit_shard_prefix_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), tab.data_ptr(), 2 * k,
+                                   commit=True, stream=s)
+        torch.cuda.synchronize()
+        out.append((idx[:R].cpu().numpy(), dl.cpu().numpy(), tab.cpu().numpy()))
+    fc, fm, ov = a.table()
+    conn.send((rank, out, fc, fm, a.peer_last_timeout))
+    peer_conn.send("done")
+    peer_conn.recv()
+    a.peer_detach()
+    a.close()
+
+
+def test_world2_prefix_commit_rank_major(oracle_c, egpu):
+    """Two ranks (two processes on cuda:0): the concatenation of the shards in rank order must be
+    exactly the single-batch prefix-commit of the oracle; both ranks end with the same table."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    a_conn, b_conn = ctx.Pipe()
+    res0_r, res0_w = ctx.Pipe(False)
+    res1_r, res1_w = ctx.Pipe(False)
+    p0 = ctx.Process(target=_prefix_rank_main, args=(0, 2, res0_w, a_conn))
+    p1 = ctx.Process(target=_prefix_rank_main, args=(1, 2, res1_w, b_conn))
+    p0.start()
+    p1.start()
+    assert res0_r.poll(180) and res1_r.poll(180), "ranks did not finish"
+    r0, r1 = res0_r.recv(), res1_r.recv()
+    p0.join(60)
+    p1.join(60)
+    assert p0.exitcode == 0 and p1.exitcode == 0
+    assert r0[4] == 0 and r1[4] == 0, "a kernel timed out waiting for its peer"
+    D = 8
+    cur_c, cur_m = PREFIX_FC, PREFIX_FM
+    cuts_in_rank1 = 0
+    for k, (n0, n1, fresh) in enumerate(PREFIX_STEPS):
+        if fresh:
+            cur_c, cur_m = PREFIX_FC, PREFIX_FM
+        rc, rm = _prefix_requests(k, n0 + n1)
+        o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(cur_c, cur_m, rc, rm)
+        i0, d0, t0 = r0[1][k]
+        i1, d1, t1 = r1[1][k]
+        assert np.array_equal(i0, o_idx[:n0]), f"rank 0 step {k}"
+        assert np.array_equal(i1, o_idx[n0:]), f"rank 1 step {k}"
+        assert np.array_equal(d0, _rank_partial(o_idx[:n0], rc[:n0], rm[:n0], D)), k
+        assert np.array_equal(d1, _rank_partial(o_idx[n0:], rc[n0:], rm[n0:], D)), k
+        assert np.array_equal(d0 + d1, np.concatenate([o_dc, o_dm])), k
+        assert np.array_equal(t0, o_tab) and np.array_equal(t1, o_tab), k
+        assert not o_tab[2 * D:].any()
+        cuts_in_rank1 += int((o_idx[n0:] >= 0).any() and (o_idx[n0:] == -2).any())
+        cur_c, cur_m = o_tab[:D].copy(), o_tab[D:2 * D].copy()
+    assert cuts_in_rank1 >= 3, "the cases must put some cuts inside rank 1's shard"
+    for res in (r0, r1):
+        assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)

@@ -96,3 +96,92 @@ def test_combine_demands_matches_oracle_apply(egpu, oracle_np):
     g[:, :16] = rng.integers(0, 60, (4, 16))
     tot = g.sum(axis=0)
     assert np.array_equal(sharding.combine_demands(fc, fm, g), oracle_np.apply_delta(fc, fm, tot[:16], tot[16:]))
+
+
+# -- prefix-commit over shards: rank-major base offsets (host logic; the CUDA path is
+#    tests/test_gpu_peer_exchange.py::test_world2_prefix_commit_rank_major).  The two helpers
+#    below restate prefix_base_kernel / prefix_cut_kernel with numpy: checker code, kept out of
+#    the product package on purpose -----------------------------------------------------------
+def prefix_base(gathered_uncapped, rank: int) -> np.ndarray:
+    """Demand (int64[2*D]) already on the running sums when rank `rank`'s first row is
+    considered: the UNCAPPED demand vectors of the lower ranks, summed.  Test-side restatement of prefix_base_kernel."""
+    g = np.asarray(gathered_uncapped, dtype=np.int64)
+    return g[:rank].sum(axis=0) if rank > 0 else np.zeros(g.shape[1], dtype=np.int64)
+
+
+def prefix_cut_shard(free_core, free_mem, idx, req_core, req_mem, base):
+    """Test-side restatement of prefix_cut/apply_kernel for one shard: rows whose device's running
+    demand (base + the rows of this shard up to and including it, committed or not) exceeds
+    free[d] become -2.  Returns (idx', committed int64[2*D])."""
+    fc = np.asarray(free_core, dtype=np.int64)
+    fm = np.asarray(free_mem, dtype=np.int64)
+    D = fc.size
+    idx = np.asarray(idx, dtype=np.int32)
+    rc = np.asarray(req_core, dtype=np.int64)
+    rm = np.asarray(req_mem, dtype=np.int64)
+    base = np.asarray(base, dtype=np.int64)
+    out = idx.copy()
+    committed = np.zeros(2 * D, dtype=np.int64)
+    for d in range(D):
+        sel = idx == d
+        pc = base[d] + np.cumsum(np.where(sel, rc, 0))
+        pm = base[D + d] + np.cumsum(np.where(sel, rm, 0))
+        ok = sel & (pc <= fc[d]) & (pm <= fm[d])
+        out[sel & ~ok] = -2
+        committed[d] = rc[ok].sum()
+        committed[D + d] = rm[ok].sum()
+    return out, committed
+
+
+def _prefix_case(total_rows):
+    rng = np.random.default_rng(total_rows)
+    fc = np.array([100, 100, 70, 30, 100, 50, 100, 100], dtype=np.int32)
+    fm = np.array([183359, 183359, 183359, 60, 183359, 183359, 183359, 183359], dtype=np.int32)
+    cls = rng.integers(0, 4, total_rows)
+    core = np.select([cls == 0, cls == 1, cls == 2], [rng.integers(1, 5, total_rows), rng.integers(31, 35, total_rows),
+                                                      rng.integers(51, 55, total_rows)], 0).astype(np.int32)
+    mem = rng.integers(1, 9, total_rows).astype(np.int32)
+    return fc, fm, core, mem
+
+
+def _prefix_worker(rank, world, port, total_rows, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from elastic_gpu_agent_b200 import sharding
+        from oracle import oracle_c
+        fc, fm, core, mem = _prefix_case(total_rows)
+        lo, hi = sharding.shard_bounds(total_rows, world, rank)
+        rc, rm = core[lo:hi], mem[lo:hi]
+        idx, dc, dm, _ = oracle_c.snapshot(fc, fm, rc, rm)                       # the scan of this shard
+        uncapped = sharding.gather_demands(torch.from_numpy(np.concatenate([dc, dm])), world)   # exchange step 1
+        base = prefix_base(uncapped.numpy(), rank)
+        idx2, committed = prefix_cut_shard(fc, fm, idx, rc, rm, base)
+        gathered = sharding.gather_demands(torch.from_numpy(committed), world)   # exchange step 2
+        tab = sharding.combine_demands(fc, fm, gathered.numpy())
+        q.put((rank, idx2.tolist(), committed.tolist(), tab.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total_rows", [(2, 40), (2, 2001), (3, 95)])
+def test_prefix_commit_rank_major_matches_unsharded_oracle(world, total_rows, oracle_c):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_prefix_worker, args=(r, world, port, total_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    fc, fm, core, mem = _prefix_case(total_rows)
+    o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(fc, fm, core, mem)
+    assert sum((r[1] for r in res), []) == o_idx.tolist()
+    assert np.array_equal(np.sum([r[2] for r in res], axis=0), np.concatenate([o_dc, o_dm]))
+    for r in res:
+        assert r[3] == o_tab.tolist()
+    assert (o_idx == -2).any() and (o_idx >= 0).any()
