@@ -508,8 +508,9 @@ int egpu_table_set_locked(egpu_ctx* ctx, const int32_t* free_core, const int32_t
     h.cand_mask = kCandMask;
     fill_sorted(h);
     // pageable source: the copy is staged before the call returns
-    // only the table part: the epilogue slots that follow stay as the device left them
-    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, offsetof(DevState, epi), cudaMemcpyHostToDevice, ctx->stream));
+    // only the table part: the peer configuration (egpu_peer_attach) and the epilogue slots
+    // that follow stay as they are
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, &h, offsetof(DevState, peer), cudaMemcpyHostToDevice, ctx->stream));
     EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->D = D;
     ctx->has_table = true;
