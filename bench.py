@@ -441,6 +441,48 @@ def main():
             etab = sharding.combine_demands(w["free_core"], w["free_mem"], np.concatenate([tot_c, tot_m])[None, :])
             parity = parity and bool(np.array_equal(ring[b][4].cpu().numpy(), etab))
 
+    # ---- untimed: prefix-commit over the shards (rank-major row order), N > 1 only --------
+    prefix_shard = None
+    if use_peer and world > 1:
+        def mix(seed, n):  # request classes that fill different devices at different rows (tests/test_gpu_peer_exchange.py)
+            rng = np.random.default_rng(seed)
+            cls = rng.integers(0, 4, n)
+            core = np.select([cls == 0, cls == 1, cls == 2], [rng.integers(1, 5, n), rng.integers(31, 35, n), rng.integers(51, 55, n)], 0)
+            return core.astype(np.int32), rng.integers(1, 9, n).astype(np.int32)
+        pfc = np.array([100, 100, 70, 30, 100, 50, 100, 100], dtype=np.int32)
+        pfm = np.array([183359, 183359, 183359, 60, 183359, 183359, 183359, 183359], dtype=np.int32)
+        torch.cuda.synchronize()
+        barrier()
+        ok = True
+        for k, per_rank in enumerate([6, 100_000]):
+            rows = [per_rank + g for g in range(world)]           # ragged on purpose
+            lo = sum(rows[:rank])
+            arc, arm = mix(77 + k, sum(rows))
+            alloc.set_table(pfc, pfm)
+            barrier()
+            with torch.cuda.stream(stream):
+                c_t = torch.from_numpy(np.ascontiguousarray(arc[lo:lo + rows[rank]])).to(dev)
+                m_t = torch.from_numpy(np.ascontiguousarray(arm[lo:lo + rows[rank]])).to(dev)
+                i_t = torch.empty(rows[rank] + 4, dtype=torch.int32, device=dev)
+                d_t = torch.zeros(16, dtype=torch.int64, device=dev)
+                t_t = torch.zeros(24, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            alloc.bestfit_shard_prefix_dev(c_t.data_ptr(), m_t.data_ptr(), rows[rank], i_t.data_ptr(), d_t.data_ptr(), t_t.data_ptr(),
+                                           (1 << 20) + 2 * k, commit=True, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            from oracle import oracle_c
+            o_idx, o_dc, o_dm, o_tab = oracle_c.prefix_commit(pfc, pfm, arc, arm)
+            mine_ok = bool(np.array_equal(i_t[:rows[rank]].cpu().numpy(), o_idx[lo:lo + rows[rank]])
+                           and np.array_equal(t_t.cpu().numpy(), o_tab) and alloc.peer_last_timeout == 0)
+            flag = torch.tensor([1 if mine_ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = ok and bool(flag.item())
+        prefix_shard = {"bit_exact_all_ranks": ok, "rows_per_rank": "6+g and 100000+g (two batches)",
+                        "note": "egpu_bestfit_batch_shard_prefix_dev: every rank checks its shard and table' against the "
+                                "oracle's single-batch prefix-commit of the concatenated rows"}
+        alloc.set_table(w["free_core"], w["free_mem"])
+        barrier()
+
     # ---- end-to-end leg: host buffers through the C ABI -----------------------
     e2e = None
     e2e_R = R
@@ -680,6 +722,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
             "parity_vs_oracle": parity,
+            "prefix_commit_over_shards": prefix_shard,
             "sweep": sweep,
             "next_rows": extra,
         }
