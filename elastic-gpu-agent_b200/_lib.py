@@ -75,6 +75,10 @@ def load() -> C.CDLL:
         "egpu_table_get": (C.c_int, [vp, i32p, i32p, i32p]),
         "egpu_table_size": (C.c_int, [vp]),
         "egpu_bestfit_batch": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int]),
+        "egpu_bestfit_batch_rounds": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int64)]),
+        "egpu_bestfit_batch_rounds_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, C.c_int32, C.POINTER(C.c_int32),
+                                                    C.POINTER(C.c_int64), vp]),
         "egpu_bestfit_batch_packed": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int]),
         "egpu_bestfit_batch_packed_dev": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int, vp]),
         "egpu_host_alloc": (C.c_int, [vp, C.POINTER(vp), C.c_int64]),

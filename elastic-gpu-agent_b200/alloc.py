@@ -121,6 +121,38 @@ class BestFitAllocator:
         self._check(rc, "egpu_bestfit_batch")
         return idx, dc, dm
 
+    def bestfit_rounds(self, req_core, req_mem, max_rounds: int = 1 << 20):
+        """egpu_bestfit_batch_rounds: committing prefix-commit rounds until nothing is deferred.
+        Returns (idx, delta_core, delta_mem, rounds, still_deferred)."""
+        rc_, rm_ = _i32(req_core), _i32(req_mem)
+        if rc_.shape != rm_.shape or rc_.ndim != 1:
+            raise L.EgpuError(L.ERR_INVALID, "bestfit_rounds")
+        D = self._lib.egpu_table_size(self._h)
+        if D < 0:
+            raise L.EgpuError(D, "egpu_table_size")
+        R = rc_.size
+        idx = np.empty(R, dtype=np.int32)
+        dc = np.zeros(D, dtype=np.int64)
+        dm = np.zeros(D, dtype=np.int64)
+        rounds, left = C.c_int32(0), C.c_int64(0)
+        rc = self._lib.egpu_bestfit_batch_rounds(self._h, _ptr(rc_), _ptr(rm_), R, _ptr(idx), _ptr(dc), _ptr(dm),
+                                                 int(max_rounds), C.byref(rounds), C.byref(left))
+        self._check(rc, "egpu_bestfit_batch_rounds")
+        return idx, dc, dm, int(rounds.value), int(left.value)
+
+    def bestfit_rounds_dev(self, d_core: int, d_mem: int, R: int, d_idx: int, max_rounds: int = 1 << 20,
+                           stream: int | None = None):
+        """Device-array form; returns (delta int64[2*D], rounds, still_deferred)."""
+        D = self._lib.egpu_table_size(self._h)
+        if D < 0:
+            raise L.EgpuError(D, "egpu_table_size")
+        delta = np.zeros(2 * D, dtype=np.int64)
+        rounds, left = C.c_int32(0), C.c_int64(0)
+        rc = self._lib.egpu_bestfit_batch_rounds_dev(self._h, C.c_void_p(d_core), C.c_void_p(d_mem), int(R), C.c_void_p(d_idx),
+                                                     _ptr(delta), int(max_rounds), C.byref(rounds), C.byref(left), _stream(stream))
+        self._check(rc, "egpu_bestfit_batch_rounds_dev")
+        return delta, int(rounds.value), int(left.value)
+
     def bestfit_raw(self, p_core: int, p_mem: int, R: int, p_idx: int, p_dc: int, p_dm: int, commit: bool = False):
         """Same call on raw host addresses (e.g. pinned buffers from host_alloc)."""
         rc = self._lib.egpu_bestfit_batch(self._h, C.c_void_p(p_core), C.c_void_p(p_mem), R, C.c_void_p(p_idx),

@@ -252,6 +252,82 @@ int launch_prefix_commit(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm
     return EGPU_OK;
 }
 
+// Rounds of committing prefix-commit until nothing is deferred (spec 2.5, "rounds").  Round 1
+// runs on the caller's device arrays; the rows it defers are gathered, in order, into dense
+// scratch arrays and re-submitted against the table round 1 committed, and so on.  Every round
+// needs two numbers on the host (rows still deferred, the round's committed demand), so this
+// is a synchronous host loop around asynchronous launches.
+struct DevScratch {
+    void* p = nullptr;
+    ~DevScratch() { if (p) cudaFree(p); }
+};
+
+int run_rounds(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx, int max_rounds,
+               long long* total_delta /* host [2*D] */, int32_t* rounds_out, int64_t* left_out, cudaStream_t s) {
+    const int D = ctx->D;
+    for (int j = 0; j < 2 * D; ++j) total_delta[j] = 0;
+    *rounds_out = 0;
+    *left_out = 0;
+    if (R == 0 || max_rounds < 1) return EGPU_OK;
+    struct RoundInfo {
+        unsigned long long deferred;
+        long long delta[2 * kMaxD];
+    };
+    DevScratch info_buf, tiles_buf, pool;
+    EGPU_CUDA(ctx, cudaMalloc(&info_buf.p, sizeof(RoundInfo)));
+    RoundInfo* d_info = static_cast<RoundInfo*>(info_buf.p);
+    const int64_t tiles_cap = (R + kCompactTile - 1) / kCompactTile;
+    EGPU_CUDA(ctx, cudaMalloc(&tiles_buf.p, sizeof(unsigned int) * static_cast<size_t>(tiles_cap)));
+    unsigned int* d_tiles = static_cast<unsigned int*>(tiles_buf.p);
+    // current round's arrays (round 1: the caller's) and the next round's
+    const int32_t* cur_rc = d_rc;
+    const int32_t* cur_rm = d_rm;
+    const int32_t* cur_map = nullptr;
+    int32_t* cur_idx = d_idx;
+    int64_t n = R;
+    int32_t* set[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // rc, rm, map, idx
+    int which = 0;
+    RoundInfo h{};
+    for (int round = 1;; ++round) {
+        int rc = launch_prefix_commit(ctx, cur_rc, cur_rm, n, cur_idx, d_info->delta, nullptr, EGPU_F_COMMIT, s);
+        if (rc != EGPU_OK) return rc;
+        if (cur_map) {
+            int64_t blocks = (n + 255) / 256;
+            if (blocks > static_cast<int64_t>(ctx->sm_count) * 8) blocks = static_cast<int64_t>(ctx->sm_count) * 8;
+            round_writeback_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(cur_idx, cur_map, n, d_idx);
+            ctx->launches += 1;
+        }
+        const int64_t tiles = (n + kCompactTile - 1) / kCompactTile;
+        deferred_count_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(cur_idx, n, d_tiles);
+        deferred_scan_kernel<<<1, 1024, 0, s>>>(d_tiles, tiles, &d_info->deferred);
+        ctx->launches += 2;
+        EGPU_CUDA(ctx, cudaGetLastError());
+        EGPU_CUDA(ctx, cudaMemcpyAsync(&h, d_info, sizeof h, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int j = 0; j < 2 * D; ++j) total_delta[j] += h.delta[j];
+        *rounds_out = round;
+        *left_out = static_cast<int64_t>(h.deferred);
+        if (h.deferred == 0 || round >= max_rounds) return EGPU_OK;
+        if (!pool.p) {  // the first round's deferred count bounds every later round
+            const size_t per = (sizeof(int32_t) * static_cast<size_t>(h.deferred) + 255) & ~static_cast<size_t>(255);
+            EGPU_CUDA(ctx, cudaMalloc(&pool.p, per * 8));
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 4; ++b) set[a][b] = reinterpret_cast<int32_t*>(static_cast<char*>(pool.p) + per * (a * 4 + b));
+        }
+        int32_t** nxt = set[which];
+        deferred_scatter_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(cur_idx, cur_rc, cur_rm, cur_map, n, d_tiles, nxt[0], nxt[1],
+                                                                               nxt[2]);
+        ctx->launches += 1;
+        EGPU_CUDA(ctx, cudaGetLastError());
+        cur_rc = nxt[0];
+        cur_rm = nxt[1];
+        cur_map = nxt[2];
+        cur_idx = nxt[3];
+        n = static_cast<int64_t>(h.deferred);
+        which ^= 1;
+    }
+}
+
 // Prefix-commit over row shards (one rank per GPU, rank-major row order).  Two exchange
 // steps: `step` carries the uncapped demand of every shard (pushed by the scan itself),
 // `step + 1` the committed demand after the cut (pushed by prefix_push_kernel).
@@ -615,6 +691,58 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* re
     }
     if (out_delta_core) std::memcpy(out_delta_core, ctx->h_delta, sizeof(int64_t) * D);
     if (out_delta_mem) std::memcpy(out_delta_mem, ctx->h_delta + D, sizeof(int64_t) * D);
+    return EGPU_OK;
+}
+
+int egpu_bestfit_batch_rounds(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem, int64_t R, int32_t* out_idx,
+                              int64_t* out_delta_core, int64_t* out_delta_mem, int32_t max_rounds, int32_t* out_rounds,
+                              int64_t* out_deferred) {
+    if (!ctx || R < 0 || R >= (1ll << 31) || max_rounds < 1) return EGPU_ERR_INVALID;
+    if (R > 0 && (!req_core || !req_mem || !out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_staging(ctx, R > 0 ? R : 1);
+    if (rc != EGPU_OK) return rc;
+    if (R > 0) {
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    }
+    long long total[2 * kMaxD];
+    int32_t rounds = 0;
+    int64_t left = 0;
+    rc = run_rounds(ctx, ctx->d_req_core, ctx->d_req_mem, R, ctx->d_idx, max_rounds, total, &rounds, &left, s);
+    if (rc != EGPU_OK) return rc;
+    if (R > 0) EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    const int D = ctx->D;
+    if (out_delta_core) std::memcpy(out_delta_core, total, sizeof(int64_t) * D);
+    if (out_delta_mem) std::memcpy(out_delta_mem, total + D, sizeof(int64_t) * D);
+    if (out_rounds) *out_rounds = rounds;
+    if (out_deferred) *out_deferred = left;
+    return EGPU_OK;
+}
+
+int egpu_bestfit_batch_rounds_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
+                                  int32_t* d_out_idx, int64_t* out_delta /* host [2*D] */, int32_t max_rounds,
+                                  int32_t* out_rounds, int64_t* out_deferred, void* stream) {
+    if (!ctx || R < 0 || R >= (1ll << 31) || max_rounds < 1) return EGPU_ERR_INVALID;
+    if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
+    if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    long long total[2 * kMaxD];
+    int32_t rounds = 0;
+    int64_t left = 0;
+    const int rc = run_rounds(ctx, d_req_core, d_req_mem, R, d_out_idx, max_rounds, total, &rounds, &left, s);
+    if (rc != EGPU_OK) return rc;
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    if (out_delta) std::memcpy(out_delta, total, sizeof(int64_t) * 2 * ctx->D);
+    if (out_rounds) *out_rounds = rounds;
+    if (out_deferred) *out_deferred = left;
     return EGPU_OK;
 }
 

@@ -1161,4 +1161,114 @@ prefix_push_kernel(DevState* __restrict__ st, const PrefixOut* __restrict__ pf, 
     }
 }
 
+// =============================================================================
+// Multi-round retry of the deferred rows (spec 2.5, "rounds"): order-preserving compaction
+// =============================================================================
+//
+// After a committing prefix-commit round the rows marked -2 are re-submitted, in their
+// original order, against the table that round committed.  These kernels gather them into
+// dense arrays (with the index of the caller's row each one came from) and write a later
+// round's results back.  Tiles of 1024 rows, 4 consecutive rows per thread, so positions
+// inside a tile follow the row order.
+constexpr int kCompactTile = 1024;
+
+__global__ void __launch_bounds__(256)
+deferred_count_kernel(const int32_t* __restrict__ idx, long long n, unsigned int* __restrict__ tile_count) {
+    __shared__ unsigned int sWarp[8];
+    const long long r0 = static_cast<long long>(blockIdx.x) * kCompactTile + 4ll * threadIdx.x;
+    unsigned int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c += (r0 + k < n && idx[r0 + k] == -2) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; ++w) t += sWarp[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts in place; one CTA walks them 1024 at a time
+__global__ void __launch_bounds__(1024)
+deferred_scan_kernel(unsigned int* __restrict__ tile_count, long long n_tiles, unsigned long long* __restrict__ total) {
+    __shared__ unsigned int sWarp[32];
+    __shared__ unsigned int sCarry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (long long t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const long long t = t0 + threadIdx.x;
+        const unsigned int own = t < n_tiles ? tile_count[t] : 0u;
+        unsigned int x = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) sWarp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = sWarp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            sWarp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned int before = sCarry + (warp ? sWarp[warp - 1] : 0u) + x - own;
+        if (t < n_tiles) tile_count[t] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) sCarry += sWarp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = sCarry;
+}
+
+__global__ void __launch_bounds__(256)
+deferred_scatter_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ rc, const int32_t* __restrict__ rm,
+                        const int32_t* __restrict__ map /* nullptr: the rows are the caller's own */, long long n,
+                        const unsigned int* __restrict__ tile_off, int32_t* __restrict__ out_rc, int32_t* __restrict__ out_rm,
+                        int32_t* __restrict__ out_map) {
+    __shared__ unsigned int sWarp[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = static_cast<long long>(blockIdx.x) * kCompactTile + 4ll * threadIdx.x;
+    bool f[4];
+    unsigned int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[k] = r0 + k < n && idx[r0 + k] == -2;
+        c += f[k] ? 1u : 0u;
+    }
+    unsigned int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sWarp[warp] = x;
+    __syncthreads();
+    unsigned int pos = tile_off[blockIdx.x] + x - c;
+    for (int w = 0; w < warp; ++w) pos += sWarp[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (f[k]) {
+            out_rc[pos] = rc[r0 + k];
+            out_rm[pos] = rm[r0 + k];
+            out_map[pos] = map ? map[r0 + k] : static_cast<int32_t>(r0 + k);
+            ++pos;
+        }
+    }
+}
+
+// a later round's answers (device, -1 or still -2) back to the caller's rows
+__global__ void __launch_bounds__(256)
+round_writeback_kernel(const int32_t* __restrict__ idx_k, const int32_t* __restrict__ map, long long n,
+                       int32_t* __restrict__ out_idx) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out_idx[map[i]] = idx_k[i];
+}
+
 }  // namespace egpu

@@ -146,6 +146,27 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core,
                        int64_t* out_delta_core, int64_t* out_delta_mem,
                        int commit);
 
+/* Batch allocation to a fixed point ("multi-round deferred retry").
+ * Round 1 is egpu_bestfit_batch(..., EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT); every later round
+ * re-submits the rows the previous one deferred, in their original order, against the table
+ * that round committed.  It stops when a round defers nothing or after max_rounds (>= 1).
+ * Every round places at least one row per device that still has takers, so it terminates; the
+ * table is always committed and never oversubscribed.
+ *   out_idx[r]      device index, EGPU_IDX_INFEASIBLE (in the round the row was last scored),
+ *                   or EGPU_IDX_DEFERRED when max_rounds ran out first
+ *   out_delta_*[D]  demand committed over all rounds (may be NULL)
+ *   *out_rounds     rounds run; *out_deferred = rows still deferred (both may be NULL)
+ * R < 2^31.  The _dev form takes device request/index arrays (16-byte aligned) and host
+ * out_delta[2*D]; it synchronises `stream` (each round needs its deferred count on the host). */
+int egpu_bestfit_batch_rounds(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem,
+                              int64_t R, int32_t* out_idx, int64_t* out_delta_core,
+                              int64_t* out_delta_mem, int32_t max_rounds, int32_t* out_rounds,
+                              int64_t* out_deferred);
+int egpu_bestfit_batch_rounds_dev(egpu_ctx* ctx, const int32_t* d_req_core,
+                                  const int32_t* d_req_mem, int64_t R, int32_t* d_out_idx,
+                                  int64_t* out_delta, int32_t max_rounds, int32_t* out_rounds,
+                                  int64_t* out_deferred, void* stream);
+
 /* Packed wire format, for callers bound by PCIe rather than by the scan: 5 bytes per decision
  * instead of 12.  req_packed[r] = EGPU_PACK_REQUEST(core, mem) (core in 0..127, mem in
  * 0..2^18-1; any word >= 2^25, e.g. EGPU_PACKED_INVALID, is an infeasible request);

@@ -94,6 +94,29 @@ def prefix_commit(free_core, free_mem, req_core, req_mem):
     return out, dc, dm, apply_delta(fc, fm, dc, dm)
 
 
+def rounds(free_core, free_mem, req_core, req_mem, max_rounds: int = 1 << 20):
+    """Spec §2.5 "rounds", built from prefix_commit above (independent of the C loop): returns
+    (idx, delta_core, delta_mem, free_core', free_mem', rounds, still_deferred)."""
+    fc = np.asarray(free_core, dtype=np.int64).copy()
+    fm = np.asarray(free_mem, dtype=np.int64).copy()
+    rc = np.asarray(req_core, dtype=np.int32)
+    rm = np.asarray(req_mem, dtype=np.int32)
+    out = np.empty(rc.size, dtype=np.int32)
+    rows = np.arange(rc.size)
+    tc = np.zeros(fc.size, dtype=np.int64)
+    tm = np.zeros(fc.size, dtype=np.int64)
+    n_rounds = 0
+    while rows.size and n_rounds < max_rounds:
+        idx, dc, dm, tab = prefix_commit(fc, fm, rc[rows], rm[rows])
+        out[rows] = idx
+        fc, fm = tab[:fc.size].astype(np.int64), tab[fc.size:2 * fc.size].astype(np.int64)
+        tc += dc
+        tm += dm
+        rows = rows[idx == -2]
+        n_rounds += 1
+    return out, tc, tm, fc.astype(np.int32), fm.astype(np.int32), n_rounds, int(rows.size)
+
+
 def apply_delta(free_core, free_mem, delta_core, delta_mem) -> np.ndarray:
     c = np.asarray(free_core, dtype=np.int64) - np.asarray(delta_core, dtype=np.int64)
     m = np.asarray(free_mem, dtype=np.int64) - np.asarray(delta_mem, dtype=np.int64)

@@ -180,6 +180,61 @@ int oracle_bestfit_prefix_commit(const int32_t* free_core, const int32_t* free_m
     return 0;
 }
 
+/* Rounds (spec §2.5, "multi-round deferred retry"): committing
+ * prefix-commit rounds; each round re-submits the rows the previous one deferred, in order,
+ * against the committed table.  free_core/free_mem are updated in place.  Returns the number
+ * of rounds run (>= 0) or a negative error; *left = rows still deferred. */
+int oracle_bestfit_rounds(int32_t* free_core, int32_t* free_mem, int32_t D, const int32_t* req_core,
+                          const int32_t* req_mem, int64_t R, int32_t* out_idx, int64_t* delta_core,
+                          int64_t* delta_mem, int32_t max_rounds, int64_t* left) {
+    if (oracle_table_valid(free_core, free_mem, D) != 0 || R < 0 || max_rounds < 1) return -1;
+    int64_t tc[ORACLE_MAX_DEVICES], tm[ORACLE_MAX_DEVICES];
+    memset(tc, 0, sizeof tc);
+    memset(tm, 0, sizeof tm);
+    int64_t* rows = (int64_t*)malloc(sizeof(int64_t) * (size_t)(R > 0 ? R : 1));
+    if (!rows) return -3;
+    int64_t n = R;
+    for (int64_t r = 0; r < R; ++r) rows[r] = r;
+    int rounds = 0;
+    while (n > 0 && rounds < max_rounds) {
+        int64_t run_c[ORACLE_MAX_DEVICES], run_m[ORACLE_MAX_DEVICES], dc[ORACLE_MAX_DEVICES], dm[ORACLE_MAX_DEVICES];
+        memset(run_c, 0, sizeof run_c);
+        memset(run_m, 0, sizeof run_m);
+        memset(dc, 0, sizeof dc);
+        memset(dm, 0, sizeof dm);
+        int64_t kept = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t r = rows[i];
+            int32_t d = oracle_pick(free_core, free_mem, D, req_core[r], req_mem[r]);  /* table of the round's start */
+            if (d >= 0) {
+                run_c[d] += req_core[r];
+                run_m[d] += req_mem[r];
+                if (run_c[d] <= free_core[d] && run_m[d] <= free_mem[d]) {
+                    dc[d] += req_core[r];
+                    dm[d] += req_mem[r];
+                } else {
+                    d = -2;
+                    rows[kept++] = r;
+                }
+            }
+            out_idx[r] = d;
+        }
+        for (int32_t d = 0; d < D; ++d) {  /* commit the round */
+            free_core[d] -= (int32_t)dc[d];
+            free_mem[d] -= (int32_t)dm[d];
+            tc[d] += dc[d];
+            tm[d] += dm[d];
+        }
+        n = kept;
+        ++rounds;
+    }
+    free(rows);
+    if (delta_core) memcpy(delta_core, tc, sizeof(int64_t) * (size_t)D);
+    if (delta_mem) memcpy(delta_mem, tm, sizeof(int64_t) * (size_t)D);
+    if (left) *left = n;
+    return rounds;
+}
+
 /* Sequential mode (spec §2.6).  free_core/free_mem are updated in place.
  * kind 0 = ALLOC(core=a, mem=b); kind 1 = FREE(event index a). */
 int oracle_replay(int32_t* free_core, int32_t* free_mem, int32_t D, const int32_t* kind,

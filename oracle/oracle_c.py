@@ -35,6 +35,8 @@ def load() -> C.CDLL:
         lib.oracle_bestfit_snapshot.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int]
         lib.oracle_bestfit_prefix_commit.restype = C.c_int
         lib.oracle_bestfit_prefix_commit.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, vp]
+        lib.oracle_bestfit_rounds.restype = C.c_int
+        lib.oracle_bestfit_rounds.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp]
         lib.oracle_replay.restype = C.c_int
         lib.oracle_replay.argtypes = [vp, vp, C.c_int32, vp, vp, vp, C.c_int64, vp]
         lib.oracle_device_hash.restype = C.c_int
@@ -116,6 +118,21 @@ def prefix_commit(free_core, free_mem, req_core, req_mem):
     if r != 0:
         raise ValueError(f"oracle_bestfit_prefix_commit failed: {r}")
     return idx, dc, dm, tab
+
+
+def rounds(free_core, free_mem, req_core, req_mem, max_rounds: int = 1 << 20):
+    """(idx, delta_core, delta_mem, free_core', free_mem', rounds, still_deferred) per spec §2.5 "rounds"."""
+    fc, fm = _i32(free_core).copy(), _i32(free_mem).copy()
+    rc, rm = _i32(req_core), _i32(req_mem)
+    D, R = fc.size, rc.size
+    idx = np.empty(R, dtype=np.int32)
+    dc = np.zeros(D, dtype=np.int64)
+    dm = np.zeros(D, dtype=np.int64)
+    left = np.zeros(1, dtype=np.int64)
+    r = load().oracle_bestfit_rounds(_p(fc), _p(fm), D, _p(rc), _p(rm), R, _p(idx), _p(dc), _p(dm), int(max_rounds), _p(left))
+    if r < 0:
+        raise ValueError(f"oracle_bestfit_rounds failed: {r}")
+    return idx, dc, dm, fc, fm, int(r), int(left[0])
 
 
 def snapshot_into(fc, fm, rc, rm, idx, nthreads: int):

@@ -169,6 +169,58 @@ def test_prefix_commit_kat(case, alloc):
         assert fc.tolist() == case["table_core"] and fm.tolist() == case["table_mem"] and not ov.any()
 
 
+@pytest.mark.parametrize("case", KAT["rounds"], ids=lambda c: c["name"])
+def test_rounds_kat(case, alloc):
+    for variant in (2, 3):
+        alloc.set_variant(variant)
+        alloc.set_table(case["free_core"], case["free_mem"])
+        idx, dc, dm, rounds, left = alloc.bestfit_rounds(case["req_core"], case["req_mem"], case["max_rounds"])
+        assert idx.tolist() == case["idx"]
+        assert dc.tolist() == case["delta_core"] and dm.tolist() == case["delta_mem"]
+        assert (rounds, left) == (case["rounds"], case["left"])
+        fc, fm, ov = alloc.table()
+        assert fc.tolist() == case["table_core"] and fm.tolist() == case["table_mem"] and not ov.any()
+
+
+@pytest.mark.parametrize("D,R,dist", [(8, 5_000, 3), (8, 300_001, 2), (64, 100_003, 4), (16, 2_049, 3), (3, 1_023, 2)])
+def test_rounds_match_oracle(D, R, dist, alloc, oracle_c, egpu):
+    """egpu_bestfit_batch_rounds to the fixed point: indices, total committed demand, final table,
+    number of rounds - all bit-exact against the oracle; then capped at 2 rounds."""
+    w = egpu.synth.workload("cfg4" if D == 64 else "cfg3")
+    rng = np.random.default_rng(D * 1000 + R)
+    fc = w["free_core"][:D] if D <= len(w["free_core"]) else rng.integers(0, 101, D).astype(np.int32)
+    fm = w["free_mem"][:D] if D <= len(w["free_mem"]) else rng.integers(0, 100000, D).astype(np.int32)
+    rc, rm = egpu.synth.requests(dist, 11, R)
+    rm = np.minimum(rm, 4096).astype(np.int32)      # small memory asks: many rows fit, many rounds
+    rc = np.minimum(rc, 7).astype(np.int32)
+    for cap in (1 << 20, 2):
+        alloc.set_table(fc, fm)
+        idx, dc, dm, rounds, left = alloc.bestfit_rounds(rc, rm, cap)
+        o_idx, o_dc, o_dm, o_fc, o_fm, o_rounds, o_left = oracle_c.rounds(fc, fm, rc, rm, cap)
+        assert (rounds, left) == (o_rounds, o_left)
+        assert np.array_equal(idx, o_idx)
+        assert np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+        g_fc, g_fm, ov = alloc.table()
+        assert np.array_equal(g_fc, o_fc) and np.array_equal(g_fm, o_fm) and not ov.any()
+    assert o_rounds == 2
+
+
+def test_rounds_dev_form(alloc, oracle_c, egpu):
+    import torch
+    w = egpu.synth.workload("cfg3")
+    R = 70_001
+    rc, rm = egpu.synth.requests(3, 5, R)
+    rc, rm = np.minimum(rc, 5).astype(np.int32), np.minimum(rm, 2048).astype(np.int32)
+    c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
+    idx = torch.empty(R, dtype=torch.int32, device="cuda")
+    alloc.set_table(w["free_core"], w["free_mem"])
+    delta, rounds, left = alloc.bestfit_rounds_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(),
+                                                   stream=torch.cuda.current_stream().cuda_stream)
+    o_idx, o_dc, o_dm, o_fc, o_fm, o_rounds, o_left = oracle_c.rounds(w["free_core"], w["free_mem"], rc, rm)
+    assert (rounds, left) == (o_rounds, o_left) and o_rounds > 2
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(delta, np.concatenate([o_dc, o_dm]))
+
+
 @pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("D,R", [(1, 5), (8, 1000), (8, 70_003), (9, 40_001), (64, 70_003), (64, 1_000_003), (8, 4_000_001)])
 def test_prefix_commit_matches_oracle(D, R, variant, alloc, oracle_c):

@@ -56,6 +56,44 @@ def test_prefix_commit_kat(case, impl, oracle_c, oracle_np):
     assert not tab[2 * D:].any()
 
 
+@pytest.mark.parametrize("case", KAT["rounds"], ids=lambda c: c["name"])
+@pytest.mark.parametrize("impl", ["c", "np"])
+def test_rounds_kat(case, impl, oracle_c, oracle_np):
+    o = oracle_c if impl == "c" else oracle_np
+    idx, dc, dm, fc, fm, rounds, left = o.rounds(case["free_core"], case["free_mem"], case["req_core"], case["req_mem"],
+                                                 case["max_rounds"])
+    assert idx.tolist() == case["idx"]
+    assert dc.tolist() == case["delta_core"] and dm.tolist() == case["delta_mem"]
+    assert fc.tolist() == case["table_core"] and fm.tolist() == case["table_mem"]
+    assert (rounds, left) == (case["rounds"], case["left"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_rounds_oracles_agree_and_reach_a_fixed_point(seed, oracle_c, oracle_np, egpu):
+    """The C loop and the numpy construction (built on prefix_commit) agree; at the fixed point no
+    row is deferred, the table is never negative, and every row reported infeasible really does
+    not fit the final table."""
+    rng = np.random.default_rng(seed)
+    D = int(rng.choice([1, 3, 8, 17, 64]))
+    fc = rng.integers(0, 101, D).astype(np.int32)
+    fm = rng.integers(0, 4096, D).astype(np.int32)
+    R = int(rng.integers(1, 400))
+    rc = rng.integers(0, 40, R).astype(np.int32)
+    rm = rng.integers(0, 600, R).astype(np.int32)
+    a = oracle_c.rounds(fc, fm, rc, rm)
+    b = oracle_np.rounds(fc, fm, rc, rm)
+    assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5:] == b[5:]
+    idx, dc, dm, tfc, tfm, rounds, left = a
+    assert left == 0 and not (idx == -2).any() and (tfc >= 0).all() and (tfm >= 0).all()
+    assert np.array_equal(tfc, fc - dc) and np.array_equal(tfm, fm - dm)
+    for r in np.flatnonzero(idx == -1):
+        # infeasible when it was last scored; the table only shrinks afterwards
+        assert not ((tfc >= rc[r]) & (tfm >= rm[r])).any()
+    capped = oracle_c.rounds(fc, fm, rc, rm, 1)
+    one = oracle_c.prefix_commit(fc, fm, rc, rm)
+    assert np.array_equal(capped[0], one[0]) and capped[5] == 1 and capped[6] == int((one[0] == -2).sum())
+
+
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg3_1m", "cfg4"])
 def test_c_oracle_matches_golden(name, oracle_c, egpu):
     g = SYN["snapshot"][name]
