@@ -1,7 +1,8 @@
 /*
  * A plain C client of the C ABI, linked against libegpu_alloc.so the way the cgo shim of
  * INTEGRATION.md would be: no Python, no C++, no CUDA headers.  Runs the cfg1 known-answer
- * vector, a GetPreferredAllocation call and a device-set hash.
+ * vector, a GetPreferredAllocation call, a device-set hash, the
+ * rounds form of the batch and a restore from one stored record.
  * Built and run by tests/test_c_client.py.  Exit code 0 = all checks passed.
  */
 #include <stdint.h>
@@ -11,6 +12,7 @@
 #include "egpu_alloc.h"
 #include "egpu_devhash.h"
 #include "egpu_plugin.h"
+#include "egpu_restore.h"
 
 #define CHECK(cond, msg)                                  \
     do {                                                  \
@@ -64,6 +66,28 @@ int main(void) {
     char h[9];
     CHECK(egpu_device_hash(ctx, one, 1, h) == EGPU_OK, "egpu_device_hash");
     printf("hash(3-07) = %s, launches = %lld\n", h, (long long)egpu_launch_count(ctx));
+
+    /* rounds: the cfg1 batch to its fixed point is the sequential answer, in two rounds */
+    for (int d = 0; d < 8; ++d) { fc[d] = 100; fm[d] = 183359; }
+    CHECK(egpu_table_set(ctx, fc, fm, 8) == EGPU_OK, "egpu_table_set (2)");
+    int32_t rounds = 0;
+    int64_t left = -1;
+    CHECK(egpu_bestfit_batch_rounds(ctx, core, mem, 5, idx, dc, dm, 16, &rounds, &left) == EGPU_OK, "egpu_bestfit_batch_rounds");
+    CHECK(idx[3] == 0 && idx[4] == 1 && rounds == 2 && left == 0 && dc[0] == 100 && dc[1] == 25, "rounds result");
+
+    /* restore: one stored record (pkg/types/pod.go:55-58) + its symlink -> 3 % less on GPU 2 */
+    const char* keys[1] = {"default/pod"};
+    const char* vals[1] = {"{\"main\":{\"Hash\":\"e4b78a7c\",\"List\":[\"0-00\",\"0-01\",\"3-07\"],"
+                           "\"ResourceName\":\"elasticgpu.io/gpu-core\"}}"};
+    int64_t klen[1] = {(int64_t)strlen(keys[0])}, vlen[1] = {(int64_t)strlen(vals[0])};
+    const char* lnames[2] = {"elastic-gpu-e4b78a7c-0", "elastic-gpuctl-e4b78a7c-0"};
+    const char* ltargets[2] = {"/dev/nvidia2", "/dev/nvidiactl"};
+    int32_t capc[4] = {100, 100, 100, 100}, capm[4] = {1000, 1000, 1000, 1000}, table[12], rstat[1];
+    int64_t counts[EGPU_REC_STATUS_COUNT];
+    CHECK(egpu_table_restore(ctx, keys, klen, vals, vlen, 1, lnames, ltargets, 2, capc, capm, 4,
+                             EGPU_RESTORE_VERIFY | EGPU_RESTORE_INSTALL, table, counts, rstat) == EGPU_OK, "egpu_table_restore");
+    CHECK(table[2] == 97 && table[0] == 100 && table[4 + 2] == 1000 && counts[EGPU_REC_OK] == 1 && rstat[0] == EGPU_REC_OK, "restore result");
+    CHECK(egpu_table_size(ctx) == 4, "restored table installed");
     egpu_ctx_destroy(ctx);
     printf("c abi client ok\n");
     return 0;
