@@ -87,9 +87,19 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         if (lut_variant) {
             const int share = ctx->lut_share;
             if (contig) {
-                l.lut_fn = bestfit_lut_kernel<256, 4, true>;
+                l.lut_fn = ctx->lut_atomic ? bestfit_lut_kernel<256, 4, true, true> : bestfit_lut_kernel<256, 4, true>;
                 l.threads = 256;
-                l.smem = sizeof(LutSmem<256, 4>);
+                l.smem = ctx->lut_atomic ? sizeof(LutSmemAtomic<256>) : sizeof(LutSmem<256, 4>);
+            } else if (ctx->lut_atomic) {  // default: demand sums through 32-bit shared-memory atomics
+                if (ctx->lut_threads == 256) {
+                    l.lut_fn = bestfit_lut_kernel<256, 4, false, true>;
+                    l.threads = 256;
+                    l.smem = sizeof(LutSmemAtomic<256>);
+                } else {
+                    l.lut_fn = bestfit_lut_kernel<128, 4, false, true>;
+                    l.threads = 128;
+                    l.smem = sizeof(LutSmemAtomic<128>);
+                }
             } else if (ctx->lut_threads == 256) {
                 l.lut_fn = share == 2 ? bestfit_lut_kernel<256, 2> : share == 8 ? bestfit_lut_kernel<256, 8> : bestfit_lut_kernel<256, 4>;
                 l.threads = 256;
@@ -484,6 +494,7 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
             const int v = std::atoi(e);
             ctx->lut_share = (v == 1 || v == 2 || v == 8) ? v : 4;
         }
+        if (const char* e = std::getenv("EGPU_LUT_ACC")) ctx->lut_atomic = std::strcmp(e, "lane") != 0;
         if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {
             const int g = std::atoi(e);
             ctx->pipe_group = g < 1 ? 1 : (g > kPipeGroupMax ? kPipeGroupMax : g);

@@ -72,6 +72,8 @@ struct egpu_ctx {
     int threads8 = 256;               // CTA size of the D <= 8 register scan (EGPU_THREADS8 = 128 | 256 | 512)
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
     int lut_threads = 256;            // CTA size of the lookup scan (EGPU_LUT_THREADS = 128 | 256)
+    bool lut_atomic = true;           // demand sums of the lookup scan through 32-bit shared-memory atomics
+                                      // (EGPU_LUT_ACC=lane: the lane-private phased sums, kept for A/B)
     int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
     // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
     void* arena = nullptr;

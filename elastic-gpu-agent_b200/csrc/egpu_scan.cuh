@@ -4,6 +4,7 @@
 // last-CTA publication, fused peer push) and the two apply kernels.  Included by
 // egpu_alloc.cu only; see DESIGN.md §4.
 #pragma once
+#include <type_traits>
 #include "egpu_kernels.cuh"
 
 namespace egpu {
@@ -601,14 +602,29 @@ struct LutSmem {
     alignas(16) unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];  // zeroed with 128-bit stores
 };
 
-template <int THREADS, int SHARE, bool CONTIG = false>
+// Alternative demand sums (ATOMIC = true): one small table per warp, updated with native 32-bit
+// shared-memory atomics (ATOMS.ADD; a 64-bit shared add is a CAS loop on sm_100a).  Three words
+// per device - core, mem & 0xffff, mem >> 16 - so that a warp can add 32 K rows before a word
+// could overflow; the words are folded into the 64-bit sWarpAcc every kLutFlushTrips trips.
+constexpr int kLutFlushTrips = 128;  // x 8 rows per thread per trip x 32 lanes = 32 K rows per warp
+template <int THREADS>
+struct LutSmemAtomic {
+    DevLut lut;
+    unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
+    int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    int sLast;
+    alignas(16) uint32_t hist32[THREADS / 32][3][kMaxD];
+};
+
+template <int THREADS, int SHARE, bool CONTIG = false, bool ATOMIC = false>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
                    const DevLut* __restrict__ glut, unsigned long long* __restrict__ tile_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& sm = *reinterpret_cast<LutSmem<THREADS, SHARE>*>(smem_raw);
+    using Smem = typename std::conditional<ATOMIC, LutSmemAtomic<THREADS>, LutSmem<THREADS, SHARE>>::type;
+    auto& sm = *reinterpret_cast<Smem*>(smem_raw);
     constexpr int LW = 32 / SHARE;  // accumulator columns per warp
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -647,7 +663,12 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
     }
     const int D = st->D;
-    {   // zero this warp's accumulators with 128-bit stores
+    if constexpr (ATOMIC) {
+        uint4* hz = reinterpret_cast<uint4*>(&sm.hist32[warp][0][0]);
+        constexpr int n16 = 3 * kMaxD * 4 / 16;
+        for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = lane; j < 2 * kMaxD; j += 32) sm.sWarpAcc[warp][j] = 0ull;
+    } else {  // zero this warp's accumulators with 128-bit stores
         uint4* hz = reinterpret_cast<uint4*>(&sm.hist[warp][0][0]);
         constexpr int n16 = (kMaxD + 1) * LW * 8 / 16;
         for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -670,7 +691,37 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     // chose the same device are merged first (the later one is redirected to the dummy row
     // with nothing to add), so the four read-modify-writes are independent and can be issued
     // as four loads, four adds, four stores per phase instead of four dependent chains.
+    // ATOMIC: fold this warp's 32-bit words into its 64-bit sums and clear them
+    auto flush32 = [&]() {
+        if constexpr (ATOMIC) {
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int d = lane + 32 * half;
+                const uint32_t hc = sm.hist32[warp][0][d], hl = sm.hist32[warp][1][d], hh = sm.hist32[warp][2][d];
+                sm.hist32[warp][0][d] = 0u;
+                sm.hist32[warp][1][d] = 0u;
+                sm.hist32[warp][2][d] = 0u;
+                sm.sWarpAcc[warp][d] += hc;
+                sm.sWarpAcc[warp][kMaxD + d] += static_cast<unsigned long long>(hl) + (static_cast<unsigned long long>(hh) << 16);
+            }
+            __syncwarp();
+        }
+    };
     auto accumulate4 = [&](const int4& r, const int4& c, const int4& m) {
+        if constexpr (ATOMIC) {
+            auto add1 = [&](int32_t i, int32_t core, int32_t mem) {
+                if (i >= 0) {  // feasible rows are inside the domain: core <= 100, mem < 2^18
+                    atomicAdd(&sm.hist32[warp][0][i], static_cast<uint32_t>(core));
+                    atomicAdd(&sm.hist32[warp][1][i], static_cast<uint32_t>(mem) & 0xffffu);
+                    if (mem >> 16) atomicAdd(&sm.hist32[warp][2][i], static_cast<uint32_t>(mem) >> 16);
+                }
+            };
+            add1(r.x, c.x, m.x);
+            add1(r.y, c.y, m.y);
+            add1(r.z, c.z, m.z);
+            add1(r.w, c.w, m.w);
+        } else {
         auto val = [](int32_t core, int32_t mem) {
             return (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
                    static_cast<unsigned long long>(static_cast<uint32_t>(mem));
@@ -702,6 +753,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
             }
             if (SHARE > 1) __syncwarp();
         }
+        }  // !ATOMIC
     };
     auto decide4 = [&](const int4& c, const int4& m) -> int4 {
         int4 r;
@@ -712,7 +764,12 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         accumulate4(r, c, m);
         return r;
     };
+    int trips = 0;
     while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: accumulate() synchronises the warp
+        if (ATOMIC && ++trips == kLutFlushTrips) {
+            flush32();
+            trips = 0;
+        }
         const long long vn = v + 2 * stride;
         const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
         int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
@@ -747,20 +804,24 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     // warp sums -> sWarpAcc, transposed: lane L adds up the LW columns of devices L and L + 32
     // (rotated start column: conflict-free), instead of three warp reductions per device
     __syncwarp();
+    if constexpr (ATOMIC) {
+        flush32();
+    } else {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int d = lane + 32 * half;
-        unsigned long long sc = 0, smem_sum = 0;
-        if (d < D) {
+        for (int half = 0; half < 2; ++half) {
+            const int d = lane + 32 * half;
+            unsigned long long sc = 0, smem_sum = 0;
+            if (d < D) {
 #pragma unroll 4
-            for (int k = 0; k < LW; ++k) {
-                const unsigned long long hv = sm.hist[warp][d + 1][(k + lane) & (LW - 1)];
-                sc += hv >> kAccShift;
-                smem_sum += hv & ((1ull << kAccShift) - 1ull);
+                for (int k = 0; k < LW; ++k) {
+                    const unsigned long long hv = sm.hist[warp][d + 1][(k + lane) & (LW - 1)];
+                    sc += hv >> kAccShift;
+                    smem_sum += hv & ((1ull << kAccShift) - 1ull);
+                }
             }
+            sm.sWarpAcc[warp][d] = sc;
+            sm.sWarpAcc[warp][kMaxD + d] = smem_sum;
         }
-        sm.sWarpAcc[warp][d] = sc;
-        sm.sWarpAcc[warp][kMaxD + d] = smem_sum;
     }
     if (boundary) {
         pdl_wait();
