@@ -710,6 +710,8 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
     };
     auto accumulate4 = [&](const int4& r, const int4& c, const int4& m) {
         if constexpr (ATOMIC) {
+            // (Measured and rejected: merging a thread's same-device requests first, 3.24 vs 3.17 us;
+            // predicated red.shared in inline PTX - ptxas gives every one its own BSSY/BRA/BSYNC.)
             auto add1 = [&](int32_t i, int32_t core, int32_t mem) {
                 if (i >= 0) {  // feasible rows are inside the domain: core <= 100, mem < 2^18
                     atomicAdd(&sm.hist32[warp][0][i], static_cast<uint32_t>(core));

@@ -1,5 +1,5 @@
-# A/B of the lookup scan's demand sums (run under gpurun): lane-private phased sums (default)
-# vs 32-bit shared-memory atomics (EGPU_LUT_ACC=atomic).  cfg4 = 64 devices x 1M requests.
+# A/B of the lookup scan's demand sums (run under gpurun): 32-bit shared-memory atomics
+# (default) vs lane-private phased sums (EGPU_LUT_ACC=lane).  cfg4 = 64 devices x 1M requests.
 run() { env "$@" python bench.py --workload cfg4 --steps 480 --warmup 20 --cpu-budget 0.1 --no-sweep > gpurun_out/b.json 2> gpurun_out/b.err; python - "$*" <<PY
 import json,sys
 try:
@@ -7,7 +7,8 @@ try:
 except Exception as ex: print(sys.argv[1], "FAILED", ex, open("gpurun_out/b.err").read()[-800:])
 PY
 }
-run EGPU_LUT_ACC=lane
 run EGPU_LUT_ACC=atomic
-for th in 128 256; do for t in 16 48 96; do run EGPU_LUT_ACC=atomic EGPU_LUT_THREADS=$th EGPU_ROWS_PER_THREAD=$t; done; done
 run EGPU_LUT_ACC=lane
+run EGPU_LUT_ACC=atomic EGPU_CTAS_PER_SM=2
+run EGPU_LUT_ACC=atomic EGPU_CTAS_PER_SM=3
+run EGPU_LUT_ACC=atomic
