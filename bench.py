@@ -654,6 +654,29 @@ def main():
             "note": "types.NewDevice + hash over every candidate container, as KubeletDeviceLocator.Locate does per container start; "
                     "C-ABI calls only (host buffers in, hashes out: H2D, sort, render, SHA-256, D2H); CPU port = qsort + SHA-256 in C, one thread"}
 
+        # rounds: prefix-commit to the fixed point (row n4), 1 M small requests on the cfg3 table
+        w3 = e.synth.workload("cfg3")
+        rrc, rrm = e.synth.requests(3, 5, 1 << 20)
+        rrc, rrm = np.minimum(rrc, 5).astype(np.int32), np.minimum(rrm, 2048).astype(np.int32)
+        alloc.set_table(w3["free_core"], w3["free_mem"])
+        alloc.bestfit_rounds(rrc[:1000], rrm[:1000])  # warm-up
+        alloc.set_table(w3["free_core"], w3["free_mem"])
+        t0 = time.perf_counter()
+        g_idx, g_dc, g_dm, g_rounds, g_left = alloc.bestfit_rounds(rrc, rrm)
+        dt_g = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o_idx, o_dc, o_dm, o_fc, o_fm, o_rounds, o_left = oracle_c.rounds(w3["free_core"], w3["free_mem"], rrc, rrm)
+        dt_c = time.perf_counter() - t0
+        t_fc, t_fm, _ = alloc.table()
+        extra["prefix_commit_rounds"] = {
+            "requests": int(rrc.size), "rounds": g_rounds, "placed": int((g_idx >= 0).sum()), "gpu_ms_e2e": 1e3 * dt_g,
+            "cpu_port_ms": 1e3 * dt_c, "cpu_threads": 1,
+            "bit_exact": bool(np.array_equal(g_idx, o_idx) and np.array_equal(g_dc, o_dc) and np.array_equal(g_dm, o_dm)
+                              and (g_rounds, g_left) == (o_rounds, o_left) and np.array_equal(t_fc, o_fc)
+                              and np.array_equal(t_fm, o_fm)),
+            "note": "egpu_bestfit_batch_rounds through the C ABI (pageable host buffers: H2D, rounds, D2H); the node holds a few "
+                    "dozen of the requests, so after round 1 the rounds are tiny and latency-bound (one host sync per round)"}
+
         # restore: the same 96 containers as stored records + symlinks -> free table (row n3)
         from elastic_gpu_agent_b200 import restore
         from oracle import restore_py
