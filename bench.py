@@ -634,13 +634,16 @@ def main():
         rng.shuffle(req)
         flat, id_off, set_off = devhash.flatten(sets)             # marshalling is not timed on either side
         flat_l, id_off_l, set_off_l = devhash.flatten([req] + sets)
-        devhash.device_hashes(alloc, sets[:2])  # warm-up
-        t0 = time.perf_counter()
-        hs = devhash.device_hashes_flat(alloc, flat, id_off, set_off)
-        dt_h = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        m = devhash.locate_flat(alloc, flat_l, id_off_l, set_off_l)
-        dt_l = time.perf_counter() - t0
+        dt_h = dt_l = None
+        for _ in range(2):  # the first full-size call grows the context's device arena: best of two
+            t0 = time.perf_counter()
+            hs = devhash.device_hashes_flat(alloc, flat, id_off, set_off)
+            dt = time.perf_counter() - t0
+            dt_h = dt if dt_h is None else min(dt_h, dt)
+            t0 = time.perf_counter()
+            m = devhash.locate_flat(alloc, flat_l, id_off_l, set_off_l)
+            dt = time.perf_counter() - t0
+            dt_l = dt if dt_l is None else min(dt_l, dt)
         calls = [oracle_c.device_hash_prepared(x) for x in sets]
         t0 = time.perf_counter()
         ref = [c[0]() for c in calls]
@@ -658,24 +661,38 @@ def main():
         w3 = e.synth.workload("cfg3")
         rrc, rrm = e.synth.requests(3, 5, 1 << 20)
         rrc, rrm = np.minimum(rrc, 5).astype(np.int32), np.minimum(rrm, 2048).astype(np.int32)
-        alloc.set_table(w3["free_core"], w3["free_mem"])
-        alloc.bestfit_rounds(rrc[:1000], rrm[:1000])  # warm-up
-        alloc.set_table(w3["free_core"], w3["free_mem"])
-        t0 = time.perf_counter()
-        g_idx, g_dc, g_dm, g_rounds, g_left = alloc.bestfit_rounds(rrc, rrm)
-        dt_g = time.perf_counter() - t0
+        dt_g = None
+        for _ in range(3):  # the first full-size call grows the staging buffers: best of three
+            alloc.set_table(w3["free_core"], w3["free_mem"])
+            t0 = time.perf_counter()
+            g_idx, g_dc, g_dm, g_rounds, g_left = alloc.bestfit_rounds(rrc, rrm)
+            dt = time.perf_counter() - t0
+            dt_g = dt if dt_g is None else min(dt_g, dt)
+        t_fc, t_fm, _ = alloc.table()
+        with torch.cuda.stream(stream):
+            rc_t, rm_t = torch.from_numpy(rrc).to(dev), torch.from_numpy(rrm).to(dev)
+            ri_t = torch.empty(rrc.size, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dt_d = None
+        for _ in range(3):
+            alloc.set_table(w3["free_core"], w3["free_mem"])
+            t0 = time.perf_counter()
+            d_delta, d_rounds, d_left = alloc.bestfit_rounds_dev(rc_t.data_ptr(), rm_t.data_ptr(), rrc.size, ri_t.data_ptr(),
+                                                                 stream=stream.cuda_stream)
+            dt = time.perf_counter() - t0
+            dt_d = dt if dt_d is None else min(dt_d, dt)
+        dev_ok = bool(np.array_equal(ri_t.cpu().numpy(), g_idx) and d_rounds == g_rounds)
         t0 = time.perf_counter()
         o_idx, o_dc, o_dm, o_fc, o_fm, o_rounds, o_left = oracle_c.rounds(w3["free_core"], w3["free_mem"], rrc, rrm)
         dt_c = time.perf_counter() - t0
-        t_fc, t_fm, _ = alloc.table()
         extra["prefix_commit_rounds"] = {
             "requests": int(rrc.size), "rounds": g_rounds, "placed": int((g_idx >= 0).sum()), "gpu_ms_e2e": 1e3 * dt_g,
-            "cpu_port_ms": 1e3 * dt_c, "cpu_threads": 1,
-            "bit_exact": bool(np.array_equal(g_idx, o_idx) and np.array_equal(g_dc, o_dc) and np.array_equal(g_dm, o_dm)
+            "gpu_ms_device_resident": 1e3 * dt_d, "cpu_port_ms": 1e3 * dt_c, "cpu_threads": 1,
+            "bit_exact": bool(dev_ok and np.array_equal(g_idx, o_idx) and np.array_equal(g_dc, o_dc) and np.array_equal(g_dm, o_dm)
                               and (g_rounds, g_left) == (o_rounds, o_left) and np.array_equal(t_fc, o_fc)
                               and np.array_equal(t_fm, o_fm)),
-            "note": "egpu_bestfit_batch_rounds through the C ABI (pageable host buffers: H2D, rounds, D2H); the node holds a few "
-                    "dozen of the requests, so after round 1 the rounds are tiny and latency-bound (one host sync per round)"}
+            "note": "egpu_bestfit_batch_rounds: through the C ABI with pageable host buffers (H2D, rounds, D2H; best of 3) and "
+                    "with device-resident arrays; every round re-scores ~1 M deferred rows (the node holds a few dozen)"}
 
         # restore: the same 96 containers as stored records + symlinks -> free table (row n3)
         from elastic_gpu_agent_b200 import restore
@@ -685,10 +702,12 @@ def main():
             recs.append(restore_py.marshal_record("default", "pod-%d" % c, {"main": (x, restore_py.MEM)}))
             lnk.append(("elastic-gpu-%s-0" % ref[c], "/dev/nvidia%d" % (c % 8)))
         capc, capm = [100] * 8, [183359] * 8
-        restore.restore_table(alloc, recs[:2], lnk, capc, capm)  # warm-up
-        t0 = time.perf_counter()
-        rfc, rfm, rov, rcounts, _ = restore.restore_table(alloc, recs, lnk, capc, capm)
-        dt_r = time.perf_counter() - t0
+        dt_r = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            rfc, rfm, rov, rcounts, _ = restore.restore_table(alloc, recs, lnk, capc, capm)
+            dt = time.perf_counter() - t0
+            dt_r = dt if dt_r is None else min(dt_r, dt)
         t0 = time.perf_counter()
         ofc, ofm, oov, ocounts, _ = restore_py.restore(recs, lnk, capc, capm)
         dt_ro = time.perf_counter() - t0
