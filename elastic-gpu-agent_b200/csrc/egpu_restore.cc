@@ -128,6 +128,21 @@ class Json {
     bool str(std::string& o) {
         o.clear();
         if (!eat('"')) return false;
+        {   // fast path (every device ID, hash and resource name): no escape before the closing quote
+            const char* q = static_cast<const char*>(std::memchr(p_, '"', static_cast<size_t>(end_ - p_)));
+            if (!q) return false;
+            bool simple = true;
+            for (const char* c = p_; c < q; ++c)
+                if (*c == '\\' || static_cast<unsigned char>(*c) < 0x20) {
+                    simple = false;
+                    break;
+                }
+            if (simple) {
+                o.assign(p_, q);
+                p_ = q + 1;
+                return true;
+            }
+        }
         while (p_ < end_) {
             const unsigned char c = static_cast<unsigned char>(*p_++);
             if (c == '"') return true;
