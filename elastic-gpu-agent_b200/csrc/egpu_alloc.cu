@@ -213,6 +213,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     if (contig) {  // one tile per CTA: make room for their sums
         if (want > ctx->tile_cap) {
             cudaFree(ctx->d_tile_sums);
+    cudaFree(ctx->d_rounds);
             ctx->d_tile_sums = nullptr;
             ctx->tile_cap = 0;
             EGPU_CUDA(ctx, cudaMalloc(&ctx->d_tile_sums, sizeof(unsigned long long) * 2 * kMaxD * static_cast<size_t>(want)));
@@ -267,9 +268,9 @@ int launch_prefix_commit(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm
 // scratch arrays and re-submitted against the table round 1 committed, and so on.  Every round
 // needs two numbers on the host (rows still deferred, the round's committed demand), so this
 // is a synchronous host loop around asynchronous launches.
-struct DevScratch {
-    void* p = nullptr;
-    ~DevScratch() { if (p) cudaFree(p); }
+struct RoundInfo {
+    unsigned long long deferred;
+    long long delta[2 * kMaxD];
 };
 
 int run_rounds(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx, int max_rounds,
@@ -279,23 +280,34 @@ int run_rounds(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t 
     *rounds_out = 0;
     *left_out = 0;
     if (R == 0 || max_rounds < 1) return EGPU_OK;
-    struct RoundInfo {
-        unsigned long long deferred;
-        long long delta[2 * kMaxD];
-    };
-    DevScratch info_buf, tiles_buf, pool;
-    EGPU_CUDA(ctx, cudaMalloc(&info_buf.p, sizeof(RoundInfo)));
-    RoundInfo* d_info = static_cast<RoundInfo*>(info_buf.p);
+    // Scratch owned by the context, grow-only, sized by R BEFORE anything is committed (a failed
+    // allocation must not leave a half-committed batch): round info, tile counts, and two sets
+    // of (core, mem, caller's row, index) arrays - the deferred rows of any round are at most R.
     const int64_t tiles_cap = (R + kCompactTile - 1) / kCompactTile;
-    EGPU_CUDA(ctx, cudaMalloc(&tiles_buf.p, sizeof(unsigned int) * static_cast<size_t>(tiles_cap)));
-    unsigned int* d_tiles = static_cast<unsigned int*>(tiles_buf.p);
+    const size_t tiles_bytes = (sizeof(unsigned int) * static_cast<size_t>(tiles_cap) + 255) & ~static_cast<size_t>(255);
+    const size_t per = (sizeof(int32_t) * static_cast<size_t>(R) + 255) & ~static_cast<size_t>(255);
+    constexpr size_t kHead = 2048;  // RoundInfo
+    const size_t need = kHead + tiles_bytes + 8 * per;
+    if (need > ctx->rounds_bytes) {
+        if (ctx->d_rounds) cudaFree(ctx->d_rounds);
+        ctx->d_rounds = nullptr;
+        ctx->rounds_bytes = 0;
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_rounds, need));
+        ctx->rounds_bytes = need;
+    }
+    static_assert(sizeof(RoundInfo) <= kHead, "round info header");
+    char* base = static_cast<char*>(ctx->d_rounds);
+    RoundInfo* d_info = reinterpret_cast<RoundInfo*>(base);
+    unsigned int* d_tiles = reinterpret_cast<unsigned int*>(base + kHead);
     // current round's arrays (round 1: the caller's) and the next round's
     const int32_t* cur_rc = d_rc;
     const int32_t* cur_rm = d_rm;
     const int32_t* cur_map = nullptr;
     int32_t* cur_idx = d_idx;
     int64_t n = R;
-    int32_t* set[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // rc, rm, map, idx
+    int32_t* set[2][4];  // rc, rm, map, idx
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b) set[a][b] = reinterpret_cast<int32_t*>(base + kHead + tiles_bytes + per * (a * 4 + b));
     int which = 0;
     RoundInfo h{};
     for (int round = 1;; ++round) {
@@ -318,12 +330,6 @@ int run_rounds(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t 
         *rounds_out = round;
         *left_out = static_cast<int64_t>(h.deferred);
         if (h.deferred == 0 || round >= max_rounds) return EGPU_OK;
-        if (!pool.p) {  // the first round's deferred count bounds every later round
-            const size_t per = (sizeof(int32_t) * static_cast<size_t>(h.deferred) + 255) & ~static_cast<size_t>(255);
-            EGPU_CUDA(ctx, cudaMalloc(&pool.p, per * 8));
-            for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 4; ++b) set[a][b] = reinterpret_cast<int32_t*>(static_cast<char*>(pool.p) + per * (a * 4 + b));
-        }
         int32_t** nxt = set[which];
         deferred_scatter_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(cur_idx, cur_rc, cur_rm, cur_map, n, d_tiles, nxt[0], nxt[1],
                                                                                nxt[2]);

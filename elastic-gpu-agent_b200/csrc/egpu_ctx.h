@@ -32,6 +32,8 @@ struct egpu_ctx {
     unsigned long long* d_tile_sums = nullptr;  // prefix-commit: per-tile per-device sums [tiles][2*64]
     int64_t tile_cap = 0;
     void* d_prefix_out = nullptr;     // PrefixOut
+    void* d_rounds = nullptr;         // scratch of egpu_bestfit_batch_rounds (grow-only)
+    size_t rounds_bytes = 0;
     DevLut* d_lut = nullptr;
     XchgBuf* d_xchg = nullptr;        // this rank's exchange buffer (exported to the peers over CUDA IPC)
     void* peer_open[kMaxRanks] = {};  // peers' buffers as opened here (nullptr for own rank)

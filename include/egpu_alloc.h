@@ -156,6 +156,8 @@ int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core,
  *                   or EGPU_IDX_DEFERRED when max_rounds ran out first
  *   out_delta_*[D]  demand committed over all rounds (may be NULL)
  *   *out_rounds     rounds run; *out_deferred = rows still deferred (both may be NULL)
+ * Scratch (32 bytes per request, kept by the context) is allocated before round 1: an
+ * allocation failure returns EGPU_ERR_NOMEM with nothing committed.
  * R < 2^31.  The _dev form takes device request/index arrays (16-byte aligned) and host
  * out_delta[2*D]; it synchronises `stream` (each round needs its deferred count on the host). */
 int egpu_bestfit_batch_rounds(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem,
