@@ -213,7 +213,6 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     if (contig) {  // one tile per CTA: make room for their sums
         if (want > ctx->tile_cap) {
             cudaFree(ctx->d_tile_sums);
-    cudaFree(ctx->d_rounds);
             ctx->d_tile_sums = nullptr;
             ctx->tile_cap = 0;
             EGPU_CUDA(ctx, cudaMalloc(&ctx->d_tile_sums, sizeof(unsigned long long) * 2 * kMaxD * static_cast<size_t>(want)));
@@ -539,6 +538,7 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
         if (ctx->peer_open[r]) cudaIpcCloseMemHandle(ctx->peer_open[r]);
     cudaFree(ctx->d_xchg);
     cudaFree(ctx->d_tile_sums);
+    cudaFree(ctx->d_rounds);
     cudaFree(ctx->d_prefix_out);
     cudaFree(ctx->arena);
     cudaFree(ctx->d_state);
