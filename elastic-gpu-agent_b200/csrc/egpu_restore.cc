@@ -28,10 +28,28 @@ void egpu_note_error(egpu_ctx* ctx, const char* msg);
 
 namespace {
 
+// One container's stored Device.  The IDs of List are kept the way the device wants them - the
+// characters back to back plus the end offset of each - so that flattening a record is two bulk
+// appends, not one small string per ID (a gpu-memory container holds one ID per MiB).
 struct Entry {
     std::string container, hash, resource;
-    std::vector<std::string> list;
+    std::string ids;             // List[0] List[1] ... without separators
+    std::vector<uint32_t> ends;  // end offset of every ID in `ids`
+    bool ids_wellformed = true;  // every ID is 1..16 characters of '-' and digits
     bool is_null = false;
+    void clear_list() {
+        ids.clear();
+        ends.clear();
+        ids_wellformed = true;
+    }
+    void add_id(const char* p, size_t n) {
+        bool ok = n >= 1 && n <= 16 && ids.size() < 0xF0000000u;  // (the offsets are 32-bit per entry)
+        for (size_t i = 0; i < n; ++i) ok = ok && (p[i] == '-' || (p[i] >= '0' && p[i] <= '9'));
+        ids_wellformed = ids_wellformed && ok;
+        if (n > 64) n = 64;  // malformed anyway (the call fails below); do not hoard its bytes
+        ids.append(p, n);
+        ends.push_back(static_cast<uint32_t>(ids.size()));
+    }
 };
 
 class Json {
@@ -249,16 +267,35 @@ class Json {
             } else if (ieq(k, "ResourceName")) {
                 if (!string_or_null(e.resource)) return false;
             } else if (ieq(k, "List")) {
-                e.list.clear();
+                e.clear_list();
                 if (!lit("null")) {
                     if (!eat('[')) return false;
                     ws();
                     if (!eat(']')) {
+                        std::string id;
+                        // one ID per MiB: size the buffers once (the rest of the value bounds both)
+                        e.ids.reserve(static_cast<size_t>(end_ - p_));
+                        e.ends.reserve(static_cast<size_t>(end_ - p_) / 4 + 1);
                         for (;;) {
-                            std::string id;
                             ws();
-                            if (!str(id)) return false;
-                            e.list.push_back(std::move(id));
+                            // fast path: "<up to 16 of '-' and digits>" straight into the entry's buffers;
+                            // with 20 bytes left the scan needs no bounds checks
+                            bool taken = false;
+                            if (end_ - p_ >= 20 && *p_ == '"' && e.ids.size() < 0xF0000000u) {
+                                const char* b = p_ + 1;
+                                const char* c = b;
+                                while (c - b < 17 && (*c == '-' || (*c >= '0' && *c <= '9'))) ++c;
+                                if (*c == '"' && c > b && c - b <= 16) {
+                                    e.ids.append(b, static_cast<size_t>(c - b));
+                                    e.ends.push_back(static_cast<uint32_t>(e.ids.size()));
+                                    p_ = c + 1;
+                                    taken = true;
+                                }
+                            }
+                            if (!taken) {  // anything else: the general string reader, then the same checks
+                                if (!str(id)) return false;
+                                e.add_id(id.data(), id.size());
+                            }
                             ws();
                             if (eat(',')) continue;
                             if (eat(']')) break;
@@ -358,15 +395,12 @@ extern "C" int egpu_table_restore(egpu_ctx* ctx, const char* const* keys, const 
             int32_t res = EGPU_RESOURCE_FOREIGN;
             if (e.resource == "elasticgpu.io/gpu-core") res = EGPU_RESOURCE_CORE;
             else if (e.resource == "elasticgpu.io/gpu-memory") res = EGPU_RESOURCE_MEM;
-            if (e.is_null) res = EGPU_RESOURCE_CORE, e.list.clear();  // a nil *Device holds nothing: reported EMPTY
+            if (e.is_null) res = EGPU_RESOURCE_CORE, e.clear_list();  // a nil *Device holds nothing: reported EMPTY
             if (res != EGPU_RESOURCE_FOREIGN) {
-                for (const std::string& id : e.list) {
-                    bool ok = !id.empty() && id.size() <= 16;
-                    for (char c : id) ok = ok && (c == '-' || (c >= '0' && c <= '9'));
-                    if (!ok) return fail(ctx, EGPU_ERR_PARSE, "device ID is not \"<gpu>-<unit>\"", r);
-                    flat.insert(flat.end(), id.begin(), id.end());
-                    id_off.push_back(static_cast<int64_t>(flat.size()));
-                }
+                if (!e.ids_wellformed) return fail(ctx, EGPU_ERR_PARSE, "device ID is not \"<gpu>-<unit>\"", r);
+                const int64_t base = static_cast<int64_t>(flat.size());
+                flat.insert(flat.end(), e.ids.begin(), e.ids.end());
+                for (uint32_t end : e.ends) id_off.push_back(base + static_cast<int64_t>(end));
             }
             set_off.push_back(static_cast<int64_t>(id_off.size()) - 1);
             char h[8];

@@ -21,7 +21,7 @@ G = json.load(open(os.path.join(HERE, "golden", "restore_records.json")))
 @pytest.fixture(scope="module")
 def harness():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O3", "-Wall", "-Werror", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "elastic-gpu-agent_b200", "csrc", "egpu_restore.cc"), os.path.join(HERE, "restore_host_harness.cc"),
            "-o", SO]
     r = subprocess.run(cmd, capture_output=True, text=True)
