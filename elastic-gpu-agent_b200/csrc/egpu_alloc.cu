@@ -452,7 +452,7 @@ void* mapped_alias(const void* p) {
 
 extern "C" {
 
-int egpu_abi_version(void) { return 1000; }
+int egpu_abi_version(void) { return 1003; }  // 1.3: + restore, sharded prefix-commit, rounds (additive)
 
 const char* egpu_strerror(int code) {
     switch (code) {

@@ -116,14 +116,18 @@ typedef struct egpu_ctx egpu_ctx;
 int  egpu_ctx_create(int cuda_device, egpu_ctx** out);
 void egpu_ctx_destroy(egpu_ctx* ctx);
 const char* egpu_strerror(int code);
-/* last CUDA error string seen by this context ("" if none) */
+/* last error detail recorded by this context ("" if none): the failing CUDA call, or the
+ * record a parse error was found in.  The pointer stays valid for the life of the context;
+ * the text is overwritten by the next failing call. */
 const char* egpu_last_error(egpu_ctx* ctx);
 /* 1 = CUDA sm_100a path.  (0 is reserved; this library never returns it.) */
 int  egpu_backend(egpu_ctx* ctx);
 /* number of kernels this context has launched since creation */
 int64_t egpu_launch_count(egpu_ctx* ctx);
 int  egpu_set_variant(egpu_ctx* ctx, int variant);
-/* bytes of ABI version: major*1000+minor */
+/* ABI version: major*1000 + minor.  Minor revisions only add entry points (1.1 placement
+ * restore, 1.2 prefix-commit over row shards, 1.3 rounds); a caller built against 1.0 keeps
+ * working. */
 int  egpu_abi_version(void);
 
 /* ---- capacity table --------------------------------------------------- */
