@@ -146,6 +146,13 @@ def cpu_port_rate(w, e, R, nthreads, budget_s):
     return n * R / dt, n
 
 
+def workload_label(name, D, R):
+    """config.workload, identical in both arms."""
+    if name == "cfg3_1m":
+        return f"{name}: {D} devices x {R} requests per GPU per step (BASELINE metric's largest single-GPU table)"
+    return f"{name}: {D} devices x {R} requests per GPU per step"
+
+
 def run_reference(args, w, e, rank, world):
     """The reference arm: the CPU implementation of the path on the host cores.  The
     reference itself has no best-fit loop and Go is not installed, so
@@ -172,8 +179,10 @@ def run_reference(args, w, e, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "D": int(w["D"]), "requests_per_step": R,
-                   "note": "CPU port of the builder-defined best-fit spec; the reference repo has no such loop and no Go toolchain is present"},
+        "config": {"workload": workload_label(args.workload, int(w["D"]), R), "D": int(w["D"]), "requests_per_step_per_gpu": R,
+                   "mode": "snapshot",
+                   "note": "CPU port of the builder-defined best-fit spec on the host cores (one host whatever --gpus says: R requests "
+                           "per step); the reference repo has no such loop and no Go toolchain is present"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {R} requests, OpenMP over request rows"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -741,9 +750,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "wall_ms_per_step_crosscheck": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {D} devices x {R} requests per GPU per step "
-                                   "(BASELINE metric's largest single-GPU table)" if args.workload == "cfg3_1m"
-                       else f"{args.workload}: {D} devices x {R} requests per GPU per step",
+            "config": {"workload": workload_label(args.workload, D, R),
                        "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
                        "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
                              if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
