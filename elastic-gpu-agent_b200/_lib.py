@@ -40,6 +40,15 @@ EV_ALLOC = 0
 EV_FREE = 1
 
 
+MAX_BATCHES = 64
+
+
+class Batch(C.Structure):
+    """egpu_batch of include/egpu_alloc.h"""
+    _fields_ = [("d_req_core", C.c_void_p), ("d_req_mem", C.c_void_p), ("R", C.c_int64), ("d_out_idx", C.c_void_p),
+                ("d_delta", C.c_void_p), ("d_table_out", C.c_void_p)]
+
+
 class EgpuError(RuntimeError):
     def __init__(self, code: int, what: str, detail: str = ""):
         self.code = code
@@ -96,6 +105,11 @@ def load() -> C.CDLL:
         "egpu_table_apply_peers_dev": (C.c_int, [vp, C.c_uint64, vp, C.c_int, vp]),
         "egpu_table_apply_peers_multi_dev": (C.c_int, [vp, C.c_uint64, C.c_int, vp, C.c_int, vp]),
         "egpu_peer_last_timeout": (C.c_int64, [vp]),
+        "egpu_bestfit_batches_dev": (C.c_int, [vp, vp, C.c_int32, C.c_int, vp]),
+        "egpu_bestfit_batches_shard_dev": (C.c_int, [vp, vp, C.c_int32, C.c_int, C.c_uint64, vp]),
+        "egpu_peer_gate_dev": (C.c_int, [vp, vp]),
+        "egpu_peer_gate_open": (C.c_int, [vp]),
+        "egpu_bestfit_query": (C.c_int, [vp, i32p, i32p, C.c_int32, vp, vp, C.c_int64, vp]),
         "egpu_device_hash_batch": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp]),
         "egpu_device_hash": (C.c_int, [vp, vp, C.c_int64, vp]),
         "egpu_device_locate": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int64)]),

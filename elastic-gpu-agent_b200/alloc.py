@@ -213,6 +213,45 @@ class BestFitAllocator:
                                               _stream(stream))
         self._check(rc, "egpu_bestfit_batch_dev")
 
+    @staticmethod
+    def make_batches(batches):
+        """(d_core, d_mem, R, d_idx, d_delta, d_table_out) tuples -> the egpu_batch array of the C ABI
+        (build it once and pass it to bestfit_batches_dev / bestfit_batches_shard_dev)."""
+        arr = (L.Batch * len(batches))()
+        for k, (c, m, R, i, dl, to) in enumerate(batches):
+            arr[k] = L.Batch(c or None, m or None, int(R), i or None, dl or None, to or None)
+        return arr
+
+    def bestfit_batches_dev(self, batches, stream: int | None = None, inputs_ready: bool = False):
+        """egpu_bestfit_batches_dev: up to 64 batches scored against the current table in one launch."""
+        arr = batches if isinstance(batches, C.Array) else self.make_batches(batches)
+        rc = self._lib.egpu_bestfit_batches_dev(self._h, arr, len(arr), L.F_INPUTS_READY if inputs_ready else 0, _stream(stream))
+        self._check(rc, "egpu_bestfit_batches_dev")
+
+    def bestfit_batches_shard_dev(self, batches, first_step: int, stream: int | None = None, inputs_ready: bool = False):
+        """K sharded steps in one launch: batch k = exchange step first_step + k."""
+        arr = batches if isinstance(batches, C.Array) else self.make_batches(batches)
+        rc = self._lib.egpu_bestfit_batches_shard_dev(self._h, arr, len(arr), L.F_INPUTS_READY if inputs_ready else 0,
+                                                      int(first_step), _stream(stream))
+        self._check(rc, "egpu_bestfit_batches_shard_dev")
+
+    def query(self, free_core, free_mem, req_core, req_mem) -> np.ndarray:
+        """egpu_bestfit_query: score against the table given here; the context's own table is untouched."""
+        fc, fm, rc_, rm_ = _i32(free_core), _i32(free_mem), _i32(req_core), _i32(req_mem)
+        if fc.shape != fm.shape or fc.ndim != 1 or rc_.shape != rm_.shape or rc_.ndim != 1:
+            raise L.EgpuError(L.ERR_INVALID, "query")
+        idx = np.empty(rc_.size, dtype=np.int32)
+        rc = self._lib.egpu_bestfit_query(self._h, fc.ctypes.data_as(L.i32p), fm.ctypes.data_as(L.i32p), fc.size,
+                                          _ptr(rc_), _ptr(rm_), rc_.size, _ptr(idx))
+        self._check(rc, "egpu_bestfit_query")
+        return idx
+
+    def gate_dev(self, stream: int | None = None):
+        self._check(self._lib.egpu_peer_gate_dev(self._h, _stream(stream)), "egpu_peer_gate_dev")
+
+    def gate_open(self):
+        self._check(self._lib.egpu_peer_gate_open(self._h), "egpu_peer_gate_open")
+
     def apply_deltas_dev(self, d_deltas: int, G: int, d_table_out: int = 0, commit: bool = True, stream: int | None = None):
         rc = self._lib.egpu_table_apply_deltas_dev(self._h, C.c_void_p(d_deltas), int(G),
                                                    C.c_void_p(d_table_out or None), 1 if commit else 0,

@@ -13,6 +13,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -71,6 +72,74 @@ void fill_sorted(DevState& h) {
     h.dev_packed = packed;
 }
 
+// ---- output ranges of the launches in flight (pipelined launches must not share outputs) ----
+// `r[0..n)`: drops empty ranges, sorts by address; returns the new count, or -1 when two of
+// them overlap each other.
+int prepare_ranges(egpu_ctx::Range* r, int n) {
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (r[i].hi > r[i].lo) r[m++] = r[i];
+    std::sort(r, r + m, [](const egpu_ctx::Range& a, const egpu_ctx::Range& b) { return a.lo < b.lo; });
+    for (int i = 1; i < m; ++i)
+        if (r[i].lo < r[i - 1].hi) return -1;
+    return m;
+}
+// both sorted and internally disjoint: one sweep
+bool overlaps_inflight(const std::vector<egpu_ctx::Range>& f, const egpu_ctx::Range* r, int n) {
+    size_t i = 0;
+    int k = 0;
+    while (i < f.size() && k < n) {
+        if (f[i].hi <= r[k].lo) ++i;
+        else if (r[k].hi <= f[i].lo) ++k;
+        else return true;
+    }
+    return false;
+}
+void add_inflight(egpu_ctx* ctx, const egpu_ctx::Range* r, int n) {
+    ctx->range_tmp.resize(ctx->inflight.size() + static_cast<size_t>(n));
+    std::merge(ctx->inflight.begin(), ctx->inflight.end(), r, r + n, ctx->range_tmp.begin(),
+               [](const egpu_ctx::Range& a, const egpu_ctx::Range& b) { return a.lo < b.lo; });
+    ctx->inflight.swap(ctx->range_tmp);
+}
+void new_group(egpu_ctx* ctx) {
+    ctx->group_len = 0;
+    ctx->group_mbatches = 0;
+    ctx->inflight.clear();
+}
+
+// first use of a kernel on this context: opt in to its shared-memory size, ask occupancy
+int configure_launch(egpu_ctx* ctx, SnapLaunch& l, int D, bool grid_variant, bool lut_variant, bool contig) {
+    if (l.ctas_per_sm != 0) return EGPU_OK;
+    const int bucket = D <= 8 ? 0 : D <= 16 ? 1 : D <= 32 ? 2 : 3;
+    int per_sm = 0;
+    if (lut_variant) {
+        // demand sums: ACC 1 = two unconditional packed adds into 8 rotated copies per warp
+        // (default), ACC 0 = round 1's three conditional adds (EGPU_LUT_ACC=atomic3, for A/B)
+        l.threads = 256;
+        if (ctx->lut_acc == 0) {
+            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 0> : bestfit_lut_kernel<256, false, 0>;
+            l.smem = sizeof(LutSmem<256, 0>);
+        } else {
+            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 1> : bestfit_lut_kernel<256, false, 1>;
+            l.smem = sizeof(LutSmem<256, 1>);
+        }
+        EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+        EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
+    } else {
+        l = pick_launch(D, grid_variant);
+        if (!grid_variant && !contig && bucket == 0 && ctx->threads8 != 256)  // experiment knob: CTA size of the D <= 8 scan
+            l = ctx->threads8 == 128 ? make_launch<8, 128>(false) : make_launch<8, 512>(false);
+        if (contig) {
+            l.fn = bucket == 0 ? bestfit_sorted_kernel<8, 256, true> : bucket == 1 ? bestfit_sorted_kernel<16, 256, true>
+                   : bucket == 2 ? bestfit_sorted_kernel<32, 256, true> : bestfit_sorted_kernel<64, 128, true>;
+        }
+        EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+        EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
+    }
+    l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    return EGPU_OK;
+}
+
 // user_flags: EGPU_F_COMMIT | EGPU_F_INPUTS_READY.  finalize = 0 only for the
 // chunked host pipeline (accumulate demand sums across launches).
 int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int64_t R, int32_t* d_idx,
@@ -82,49 +151,9 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
     if (contig && grid_variant) return EGPU_ERR_STATE;  // the literal variant has no prefix-commit mode
     SnapLaunch& l = ctx->snap[contig ? (lut_variant ? 4 : 3) : grid_variant ? 1 : (lut_variant ? 2 : 0)][bucket];
-    if (l.ctas_per_sm == 0) {  // first use on this context: opt in to the shared-memory size, ask occupancy
-        int per_sm = 0;
-        if (lut_variant) {
-            const int share = ctx->lut_share;
-            if (contig) {
-                l.lut_fn = ctx->lut_atomic ? bestfit_lut_kernel<256, 4, true, true> : bestfit_lut_kernel<256, 4, true>;
-                l.threads = 256;
-                l.smem = ctx->lut_atomic ? sizeof(LutSmemAtomic<256>) : sizeof(LutSmem<256, 4>);
-            } else if (ctx->lut_atomic) {  // default: demand sums through 32-bit shared-memory atomics
-                if (ctx->lut_threads == 256) {
-                    l.lut_fn = bestfit_lut_kernel<256, 4, false, true>;
-                    l.threads = 256;
-                    l.smem = sizeof(LutSmemAtomic<256>);
-                } else {
-                    l.lut_fn = bestfit_lut_kernel<128, 4, false, true>;
-                    l.threads = 128;
-                    l.smem = sizeof(LutSmemAtomic<128>);
-                }
-            } else if (ctx->lut_threads == 256) {
-                l.lut_fn = share == 2 ? bestfit_lut_kernel<256, 2> : share == 8 ? bestfit_lut_kernel<256, 8> : bestfit_lut_kernel<256, 4>;
-                l.threads = 256;
-                l.smem = share == 2 ? sizeof(LutSmem<256, 2>) : share == 8 ? sizeof(LutSmem<256, 8>) : sizeof(LutSmem<256, 4>);
-            } else {
-                l.lut_fn = share == 1 ? bestfit_lut_kernel<128, 1> : share == 2 ? bestfit_lut_kernel<128, 2>
-                           : share == 4 ? bestfit_lut_kernel<128, 4> : bestfit_lut_kernel<128, 8>;
-                l.threads = 128;
-                l.smem = share == 1 ? sizeof(LutSmem<128, 1>) : share == 2 ? sizeof(LutSmem<128, 2>)
-                         : share == 4 ? sizeof(LutSmem<128, 4>) : sizeof(LutSmem<128, 8>);
-            }
-            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
-            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
-        } else {
-            l = pick_launch(ctx->D, grid_variant);
-            if (!grid_variant && !contig && bucket == 0 && ctx->threads8 != 256)  // experiment knob: CTA size of the D <= 8 scan
-                l = ctx->threads8 == 128 ? make_launch<8, 128>(false) : make_launch<8, 512>(false);
-            if (contig) {
-                l.fn = bucket == 0 ? bestfit_sorted_kernel<8, 256, true> : bucket == 1 ? bestfit_sorted_kernel<16, 256, true>
-                       : bucket == 2 ? bestfit_sorted_kernel<32, 256, true> : bestfit_sorted_kernel<64, 128, true>;
-            }
-            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
-            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
-        }
-        l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    {
+        const int rc = configure_launch(ctx, l, ctx->D, grid_variant, lut_variant, contig);
+        if (rc != EGPU_OK) return rc;
     }
     if (lut_variant && ctx->lut_dirty) {  // refresh the lookup tables on the launching stream
         lut_build_kernel<<<1, 256, 0, s>>>(ctx->d_state, ctx->d_lut);
@@ -143,6 +172,8 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     //    this stream (EGPU_F_INPUTS_READY),
     //  - the previous launch was a scan of this context on the same stream that
     //    does not rewrite the table, and this one is a plain finalising scan,
+    //  - it does not commit (a committing launch rewrites the table the launches still in
+    //    flight read and compute their table' from: it is always fully ordered),
     //  - its outputs (indices, demand sums, table') are disjoint from the outputs
     //    of every launch since the last fully ordered one, and
     //  - fewer than pipe_group launches have been issued since then, which bounds
@@ -151,11 +182,11 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
         {reinterpret_cast<uintptr_t>(d_idx), reinterpret_cast<uintptr_t>(d_idx) + static_cast<uintptr_t>(R) * sizeof(int32_t)},
         {reinterpret_cast<uintptr_t>(d_delta), reinterpret_cast<uintptr_t>(d_delta) + (d_delta ? sizeof(long long) * 2 * ctx->D : 0)},
         {reinterpret_cast<uintptr_t>(d_table_out), reinterpret_cast<uintptr_t>(d_table_out) + (d_table_out ? sizeof(int32_t) * 3 * ctx->D : 0)}};
-    bool pipelined = !grid_variant && !contig && finalize && (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan &&
-                     !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0;
-    for (int i = 0; pipelined && i < 3 * ctx->group_len; ++i)
-        for (int k = 0; k < 3; ++k)
-            if (mine[k].lo < ctx->group_out[i].hi && ctx->group_out[i].lo < mine[k].hi) pipelined = false;
+    const int n_mine = prepare_ranges(mine, 3);
+    if (n_mine < 0) return EGPU_ERR_INVALID;  // two of this launch's own outputs overlap
+    bool pipelined = !grid_variant && !contig && finalize && (user_flags & EGPU_F_INPUTS_READY) && !(user_flags & EGPU_F_COMMIT) &&
+                     ctx->prev_is_scan && !ctx->prev_changes_table && ctx->prev_stream == s && ctx->group_len > 0 &&
+                     !overlaps_inflight(ctx->inflight, mine, n_mine);
     if (pipelined) {
         flags |= kFlagLateWait;
         if (ctx->group_len >= ctx->pipe_group) {
@@ -163,10 +194,10 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
             // for them before its epilogue and only then lets its successors start; it becomes
             // the first member of the next group
             flags |= kFlagBoundary;
-            ctx->group_len = 0;
+            new_group(ctx);
         }
     } else {
-        ctx->group_len = 0;
+        new_group(ctx);
     }
     // Early trigger (griddepcontrol.launch_dependents before the work is done) only helps when
     // the next launch is another scan of a pipelined stream, so only those launches do it.
@@ -183,7 +214,10 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
     int rpt = 8;
-    if (user_flags & EGPU_F_INPUTS_READY) rpt = (lut_variant || ctx->D <= 16) ? 48 : 8;  // measured, scripts/tune_*.sh
+    // (a launch that could not be pipelined has nothing to overlap with: it keeps the lone-launch
+    // grid even on a stream the caller declared pipelined - e.g. the first launch of a graph)
+    if ((user_flags & EGPU_F_INPUTS_READY) && (pipelined || ctx->lone_first == 0))
+        rpt = (lut_variant || ctx->D <= 16) ? 48 : 8;  // measured, scripts/tune_*.sh
     else if (lut_variant) rpt = 32;  // the lookup scan has a 13 KB per-CTA table tile to amortise
     if (rpt_hint > 0) rpt = rpt_hint;
     if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
@@ -230,10 +264,123 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     if (flags & kFlagCommit) ctx->lut_dirty = true;
     ctx->launches += 1;
     ctx->seq += 1;
-    for (int k = 0; k < 3; ++k) ctx->group_out[3 * ctx->group_len + k] = mine[k];
+    add_inflight(ctx, mine, n_mine);
     ctx->group_len += 1;
     ctx->prev_is_scan = finalize;
     ctx->prev_changes_table = (flags & kFlagCommit) != 0;
+    ctx->prev_stream = s;
+    return EGPU_OK;
+}
+
+// Multi-batch launch: K batches, all scored against the current table, one grid (CTA (b, t) =
+// tile t of batch b), one epilogue slot per batch.  Pipelines behind its predecessor under the
+// same conditions as launch_snapshot; a launch group never holds more than half of the
+// epi_multi ring, so the slots of everything that can be in flight are distinct.
+// push_base = first exchange step + 1 when every batch also pushes its demand vector to the peers.
+int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cudaStream_t s, unsigned long long push_base) {
+    if (ctx->variant == EGPU_VARIANT_GRID) return EGPU_ERR_STATE;  // the literal variant has no multi-batch form
+    const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
+    const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
+    MultiLaunch& l = ctx->multi[lut_variant ? 1 : 0][bucket];
+    if (l.ctas_per_sm == 0) {
+        int per_sm = 0;
+        if (lut_variant) {
+            l.lut_fn = ctx->lut_acc == 0 ? bestfit_lut_multi_kernel<256, 0> : bestfit_lut_multi_kernel<256, 1>;
+            l.threads = 256;
+            l.smem = ctx->lut_acc == 0 ? sizeof(LutSmem<256, 0>) : sizeof(LutSmem<256, 1>);
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
+        } else {
+            static const SortedMultiKernel fns[4] = {bestfit_sorted_multi_kernel<8, 256>, bestfit_sorted_multi_kernel<16, 256>,
+                                                     bestfit_sorted_multi_kernel<32, 256>, bestfit_sorted_multi_kernel<64, 128>};
+            static const int threads[4] = {256, 256, 256, 128};
+            static const size_t smem[4] = {sizeof(SnapSmem<8, 256>), sizeof(SnapSmem<16, 256>), sizeof(SnapSmem<32, 256>),
+                                           sizeof(SnapSmem<64, 128>)};
+            l.fn = fns[bucket];
+            l.threads = threads[bucket];
+            l.smem = smem[bucket];
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(l.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
+            EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.fn, l.threads, l.smem));
+        }
+        l.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    }
+    if (lut_variant && ctx->lut_dirty) {
+        lut_build_kernel<<<1, 256, 0, s>>>(ctx->d_state, ctx->d_lut);
+        EGPU_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        ctx->lut_dirty = false;
+        ctx->prev_is_scan = false;
+    }
+    MultiArgs args;
+    std::memset(&args, 0, sizeof args);
+    egpu_ctx::Range* mine = ctx->multi_ranges;
+    int64_t max_r = 0;
+    for (int k = 0; k < K; ++k) {
+        const egpu_batch& b = bs[k];
+        args.b[k].rc = b.d_req_core;
+        args.b[k].rm = b.d_req_mem;
+        args.b[k].idx = b.d_out_idx;
+        args.b[k].delta = reinterpret_cast<long long*>(b.d_delta);
+        args.b[k].table_out = push_base ? nullptr : b.d_table_out;  // sharded: table' comes from the apply
+        args.b[k].R = b.R;
+        if (b.R > max_r) max_r = b.R;
+        const uintptr_t pi = reinterpret_cast<uintptr_t>(b.d_out_idx), pd = reinterpret_cast<uintptr_t>(b.d_delta),
+                        pt = reinterpret_cast<uintptr_t>(args.b[k].table_out);
+        mine[3 * k] = {pi, pi + static_cast<uintptr_t>(b.R) * sizeof(int32_t)};
+        mine[3 * k + 1] = {pd, pd + (pd ? sizeof(long long) * 2 * ctx->D : 0)};
+        mine[3 * k + 2] = {pt, pt + (pt ? sizeof(int32_t) * 3 * ctx->D : 0)};
+    }
+    const int n_mine = prepare_ranges(mine, 3 * K);
+    if (n_mine < 0) return EGPU_ERR_INVALID;  // two batches of one launch share an output: their order would be undefined
+    int flags = kFlagFinalize;
+    bool pipelined = (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan && !ctx->prev_changes_table && ctx->prev_stream == s &&
+                     ctx->group_len > 0 && !overlaps_inflight(ctx->inflight, mine, n_mine);
+    if (pipelined) {
+        flags |= kFlagLateWait;
+        if (ctx->group_len >= ctx->pipe_group || ctx->group_mbatches + K > kMultiSlots - kMultiMax) {
+            flags |= kFlagBoundary;
+            new_group(ctx);
+        }
+    } else {
+        new_group(ctx);
+    }
+    if (user_flags & EGPU_F_INPUTS_READY) flags |= kFlagEarlyTrigger;
+
+    // tiles per batch: enough CTAs that a thread has >= multi_rpt rows, at most the resident
+    // capacity of the GPU shared out among the K batches
+    const int64_t nvec = max_r >> 2;
+    const int64_t per_cta = static_cast<int64_t>(l.threads) * ((ctx->multi_rpt + 3) / 4);
+    int64_t tiles = (nvec + per_cta - 1) / per_cta;
+    int per_sm = l.ctas_per_sm;
+    if (ctx->ctas_per_sm_cap > 0 && ctx->ctas_per_sm_cap < per_sm) per_sm = ctx->ctas_per_sm_cap;
+    int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * ctx->multi_waves / K;
+    if (tiles > cap) tiles = cap;
+    if (tiles < 1) tiles = 1;
+    if (max_r / (tiles * l.threads) + 8 >= (1ll << 19)) return EGPU_ERR_INVALID;  // lane-private sums hold 2^19 rows per lane
+
+    const unsigned int slot_base = static_cast<unsigned int>(ctx->mseq % kMultiSlots);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(tiles * K));
+    cfg.blockDim = dim3(static_cast<unsigned>(l.threads));
+    cfg.dynamicSmemBytes = l.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (lut_variant)
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.lut_fn, ctx->d_state, args, static_cast<int>(tiles), flags, slot_base, push_base,
+                                          static_cast<const DevLut*>(ctx->d_lut)));
+    else
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, args, static_cast<int>(tiles), flags, slot_base, push_base));
+    ctx->launches += 1;
+    ctx->mseq += static_cast<uint64_t>(K);
+    add_inflight(ctx, mine, n_mine);
+    ctx->group_len += 1;
+    ctx->group_mbatches += K;
+    ctx->prev_is_scan = true;
+    ctx->prev_changes_table = false;
     ctx->prev_stream = s;
     return EGPU_OK;
 }
@@ -414,7 +561,7 @@ int launch_packed(egpu_ctx* ctx, const uint32_t* d_req, int64_t R, signed char* 
                                       d_table_out, flags, slot));
     ctx->launches += 1;
     ctx->seq += 1;
-    ctx->group_len = 0;
+    new_group(ctx);
     ctx->prev_is_scan = false;  // the int32 scans do not pipeline behind this one
     if (flags & kFlagCommit) ctx->lut_dirty = true;
     return EGPU_OK;
@@ -452,7 +599,7 @@ void* mapped_alias(const void* p) {
 
 extern "C" {
 
-int egpu_abi_version(void) { return 1003; }  // 1.3: + restore, sharded prefix-commit, rounds (additive)
+int egpu_abi_version(void) { return 1004; }  // 1.4: + multi-batch launches, stateless query, start gate (additive)
 
 const char* egpu_strerror(int code) {
     switch (code) {
@@ -494,12 +641,10 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
             const int v = std::atoi(e);
             ctx->threads8 = (v == 128 || v == 512) ? v : 256;
         }
-        if (const char* e = std::getenv("EGPU_LUT_THREADS")) ctx->lut_threads = std::atoi(e) == 128 ? 128 : 256;
-        if (const char* e = std::getenv("EGPU_LUT_SHARE")) {
-            const int v = std::atoi(e);
-            ctx->lut_share = (v == 1 || v == 2 || v == 8) ? v : 4;
-        }
-        if (const char* e = std::getenv("EGPU_LUT_ACC")) ctx->lut_atomic = std::strcmp(e, "lane") != 0;
+        if (const char* e = std::getenv("EGPU_LUT_ACC")) ctx->lut_acc = std::strcmp(e, "atomic3") == 0 ? 0 : 1;
+        if (const char* e = std::getenv("EGPU_LONE_FIRST")) ctx->lone_first = std::atoi(e) != 0;
+        if (const char* e = std::getenv("EGPU_MULTI_WAVES")) ctx->multi_waves = std::max(1, std::min(8, std::atoi(e)));
+        if (const char* e = std::getenv("EGPU_MULTI_RPT")) ctx->multi_rpt = std::max(4, std::min(4096, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {
             const int g = std::atoi(e);
             ctx->pipe_group = g < 1 ? 1 : (g > kPipeGroupMax ? kPipeGroupMax : g);
@@ -516,6 +661,10 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         EGPU_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_delta_dev), ctx->h_delta, 0));
         if (const char* e = std::getenv("EGPU_NO_ZERO_COPY")) ctx->no_zero_copy = std::atoi(e) != 0;
         EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_table, sizeof(int32_t) * 3 * kMaxD));
+        EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_qtable, offsetof(DevState, peer)));
+        EGPU_CUDA(ctx, cudaMallocHost(&ctx->h_gate, sizeof(unsigned long long)));
+        *ctx->h_gate = 0ull;
+        EGPU_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->h_gate_dev), ctx->h_gate, 0));
         EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return EGPU_OK;
     }();
@@ -550,6 +699,9 @@ void egpu_ctx_destroy(egpu_ctx* ctx) {
     cudaFree(ctx->d_table_out);
     if (ctx->h_delta) cudaFreeHost(ctx->h_delta);
     if (ctx->h_table) cudaFreeHost(ctx->h_table);
+    if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
+    if (ctx->h_qtable) cudaFreeHost(ctx->h_qtable);
+    cudaFree(ctx->d_qstate);
     (void)cudaGetLastError();
     delete ctx;
 }
@@ -664,6 +816,114 @@ int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32
                                     flags, s);
     return launch_snapshot(ctx, d_req_core, d_req_mem, R, d_out_idx, reinterpret_cast<long long*>(d_delta),
                            d_table_out, flags, true, s);
+}
+
+static int check_batches(const egpu_batch* batches, int32_t K) {
+    if (!batches || K < 1 || K > EGPU_MAX_BATCHES) return EGPU_ERR_INVALID;
+    for (int k = 0; k < K; ++k) {
+        const egpu_batch& b = batches[k];
+        if (b.R < 0) return EGPU_ERR_INVALID;
+        if (b.R > 0 && (!b.d_req_core || !b.d_req_mem || !b.d_out_idx)) return EGPU_ERR_INVALID;
+        if (!aligned16(b.d_req_core) || !aligned16(b.d_req_mem) || !aligned16(b.d_out_idx)) return EGPU_ERR_INVALID;
+    }
+    return EGPU_OK;
+}
+
+int egpu_bestfit_batches_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags, void* stream) {
+    if (!ctx || (flags & ~EGPU_F_INPUTS_READY)) return EGPU_ERR_INVALID;
+    const int rc = check_batches(batches, K);
+    if (rc != EGPU_OK) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_multi(ctx, batches, K, flags, s, 0);
+}
+
+int egpu_bestfit_batches_shard_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags, uint64_t first_step,
+                                   void* stream) {
+    if (!ctx || (flags & ~EGPU_F_INPUTS_READY) || first_step >= (1ull << 47)) return EGPU_ERR_INVALID;
+    const int rc = check_batches(batches, K);
+    if (rc != EGPU_OK) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
+    if (!ctx->attached) return EGPU_ERR_STATE;
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return launch_multi(ctx, batches, K, flags, s, first_step + 1);
+}
+
+int egpu_peer_gate_dev(egpu_ctx* ctx, void* stream) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    gate_kernel<<<1, 32, 0, s>>>(ctx->d_state, ctx->h_gate_dev);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->prev_is_scan = false;
+    return EGPU_OK;
+}
+
+int egpu_peer_gate_open(egpu_ctx* ctx) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    __atomic_fetch_add(ctx->h_gate, 1ull, __ATOMIC_RELEASE);
+    return EGPU_OK;
+}
+
+int egpu_bestfit_query(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D, const int32_t* req_core,
+                       const int32_t* req_mem, int64_t R, int32_t* out_idx) {
+    if (!ctx || !free_core || !free_mem || D < 1 || D > EGPU_MAX_DEVICES || R < 0) return EGPU_ERR_INVALID;
+    if (R > 0 && (!req_core || !req_mem || !out_idx)) return EGPU_ERR_INVALID;
+    for (int d = 0; d < D; ++d) {
+        if (free_core[d] < 0 || free_core[d] > EGPU_CORE_MAX) return EGPU_ERR_INVALID;
+        if (free_mem[d] < 0 || free_mem[d] > EGPU_MEM_MAX) return EGPU_ERR_INVALID;
+    }
+    if (R == 0) return EGPU_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    if (!ctx->d_qstate) {
+        EGPU_CUDA(ctx, cudaMalloc(&ctx->d_qstate, sizeof(DevState)));
+        EGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_qstate, 0, sizeof(DevState), s));
+    }
+    // the scratch table: same layout and sorted view as the context's own, in its own DevState
+    DevState* h = reinterpret_cast<DevState*>(ctx->h_qtable);
+    std::memset(h, 0, offsetof(DevState, peer));
+    std::memcpy(h->free_core, free_core, sizeof(int32_t) * D);
+    std::memcpy(h->free_mem, free_mem, sizeof(int32_t) * D);
+    h->D = D;
+    h->cand_xor = kGuards;
+    h->cand_mask = kCandMask;
+    fill_sorted(*h);
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_qstate, h, offsetof(DevState, peer), cudaMemcpyHostToDevice, s));
+    int rc = ensure_staging(ctx, R);
+    if (rc != EGPU_OK) return rc;
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_core, req_core, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    EGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_req_mem, req_mem, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    // the register scan whatever the context's variant: one table, used once - lookup tables would not pay
+    const int bucket = D <= 8 ? 0 : D <= 16 ? 1 : D <= 32 ? 2 : 3;
+    SnapLaunch& l = ctx->snap[0][bucket];
+    rc = configure_launch(ctx, l, D, false, false, false);
+    if (rc != EGPU_OK) return rc;
+    const int64_t nvec = R >> 2;
+    const int64_t per_cta = static_cast<int64_t>(l.threads) * 2;
+    int64_t want = (nvec + per_cta - 1) / per_cta;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * l.ctas_per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    if (R / (want * l.threads) + 8 >= (1ll << 19)) return EGPU_ERR_INVALID;
+    // fully ordered launch (no PDL flags), epilogue slot 0 of the scratch state, nothing published
+    l.fn<<<static_cast<unsigned>(want), l.threads, l.smem, s>>>(ctx->d_qstate, ctx->d_req_core, ctx->d_req_mem,
+                                                                static_cast<long long>(R), ctx->d_idx, nullptr, nullptr,
+                                                                kFlagFinalize, 0ull, nullptr);
+    EGPU_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->prev_is_scan = false;
+    EGPU_CUDA(ctx, cudaMemcpyAsync(out_idx, ctx->d_idx, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, s));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+    return EGPU_OK;
 }
 
 int egpu_bestfit_batch(egpu_ctx* ctx, const int32_t* req_core, const int32_t* req_mem, int64_t R,
@@ -822,7 +1082,9 @@ int egpu_peer_detach(egpu_ctx* ctx) {
 
 int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
                                  int32_t* d_out_idx, int64_t* d_delta, int flags, uint64_t step, void* stream) {
-    if (!ctx || R < 0 || (flags & EGPU_F_COMMIT)) return EGPU_ERR_INVALID;  // the commit happens in apply_peers
+    // the commit happens in apply_peers; prefix-commit over shards has its own entry point;
+    // step + 1 travels in 48 bits of the launch word
+    if (!ctx || R < 0 || (flags & ~EGPU_F_INPUTS_READY) || step >= (1ull << 47)) return EGPU_ERR_INVALID;
     if (R > 0 && (!d_req_core || !d_req_mem || !d_out_idx)) return EGPU_ERR_INVALID;
     if (!aligned16(d_req_core) || !aligned16(d_req_mem) || !aligned16(d_out_idx)) return EGPU_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -866,7 +1128,7 @@ int egpu_bestfit_batch_shard_lag_dev(egpu_ctx* ctx, const int32_t* d_req_core, c
 
 int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nsteps, int32_t* const* d_table_outs,
                                      int commit, void* stream) {
-    if (!ctx || nsteps < 1 || nsteps > 8) return EGPU_ERR_INVALID;
+    if (!ctx || nsteps < 1 || nsteps > kApplyMax) return EGPU_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->has_table) return EGPU_ERR_NO_TABLE;
     if (!ctx->attached) return EGPU_ERR_STATE;
@@ -877,7 +1139,7 @@ int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nst
         ctx->prev_is_scan = false;  // the next scan must see the new table
     }
     ApplyOuts outs;
-    for (int k = 0; k < 8; ++k) outs.table_out[k] = (d_table_outs && k < nsteps) ? d_table_outs[k] : nullptr;
+    for (int k = 0; k < kApplyMax; ++k) outs.table_out[k] = (d_table_outs && k < nsteps) ? d_table_outs[k] : nullptr;
     apply_peers_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, first_step + 1, nsteps, outs, commit);
     EGPU_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <mutex>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -26,9 +27,25 @@ struct SnapLaunch {
     int ctas_per_sm = 0;  // 0 = not configured yet on this context
 };
 
+using SortedMultiKernel = void (*)(egpu::DevState*, const egpu::MultiArgs, int, int, unsigned int, unsigned long long);
+using LutMultiKernel = void (*)(egpu::DevState*, const egpu::MultiArgs, int, int, unsigned int, unsigned long long,
+                                const egpu::DevLut*);
+struct MultiLaunch {
+    SortedMultiKernel fn = nullptr;
+    LutMultiKernel lut_fn = nullptr;
+    int threads = 0;
+    size_t smem = 0;
+    int ctas_per_sm = 0;
+};
+
 struct egpu_ctx {
     std::mutex mu;
     SnapLaunch snap[5][4];            // [sorted, grid, lut, sorted CONTIG, lut CONTIG][D bucket]
+    MultiLaunch multi[2][4];          // multi-batch launches: [sorted, lut][D bucket]
+    void* h_qtable = nullptr;         // pinned host image of that table (the part of DevState before `peer`)
+    DevState* d_qstate = nullptr;     // scratch table of egpu_bestfit_query (the context's own table is not touched)
+    unsigned long long* h_gate = nullptr;      // pinned: start gates the host has opened (egpu_peer_gate_open)
+    unsigned long long* h_gate_dev = nullptr;  // its device-visible alias
     unsigned long long* d_tile_sums = nullptr;  // prefix-commit: per-tile per-device sums [tiles][2*64]
     int64_t tile_cap = 0;
     void* d_prefix_out = nullptr;     // PrefixOut
@@ -66,17 +83,25 @@ struct egpu_ctx {
     cudaStream_t prev_stream = nullptr;
     uint64_t seq = 0;                 // scans launched (epilogue slot = seq mod kEpiSlots)
     int group_len = 0;                // launches since (and including) the last fully ordered one
-    struct Range { uintptr_t lo, hi; } group_out[3 * kPipeGroupMax];  // their output ranges
+    int group_mbatches = 0;           // ... and the epi_multi slots (batches of multi-batch launches) they hold
+    uint64_t mseq = 0;                // batches launched through multi-batch launches (slot = mseq mod kMultiSlots)
+    struct Range { uintptr_t lo, hi; };
+    std::vector<Range> inflight;      // output ranges of those launches, sorted by address, pairwise disjoint
+    std::vector<Range> range_tmp;
+    Range multi_ranges[3 * kMultiMax];  // scratch of launch_multi
+    int lone_first = 1;               // a launch that cannot overlap a predecessor gets the lone-launch grid even on a
+                                      // stream declared pipelined (EGPU_LONE_FIRST=0: round 1's sizing, for A/B)
+    int multi_waves = 1;              // multi-batch launches: CTA waves the grid may hold (EGPU_MULTI_WAVES)
+    int multi_rpt = 8;                // ... and the fewest rows per thread worth a CTA (EGPU_MULTI_RPT)
     int pipe_group = 24;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     int packed_ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the packed-format scan per D bucket, 0 = not asked yet
     int threads8 = 256;               // CTA size of the D <= 8 register scan (EGPU_THREADS8 = 128 | 256 | 512)
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
-    int lut_threads = 256;            // CTA size of the lookup scan (EGPU_LUT_THREADS = 128 | 256)
-    bool lut_atomic = true;           // demand sums of the lookup scan through 32-bit shared-memory atomics
-                                      // (EGPU_LUT_ACC=lane: the lane-private phased sums, kept for A/B)
-    int lut_share = 4;                // lanes per accumulator in the lookup scan (EGPU_LUT_SHARE = 1, 2, 4)
+    int lut_acc = 1;                  // demand sums of the lookup scan: 1 = two packed unconditional shared-memory
+                                      // adds into rotated copies (default), 0 = round 1's three conditional adds
+                                      // (EGPU_LUT_ACC=atomic3, kept for A/B)
     // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
     void* arena = nullptr;
     size_t arena_cap = 0;

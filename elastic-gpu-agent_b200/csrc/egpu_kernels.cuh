@@ -58,10 +58,10 @@ constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before
 constexpr int kAccShift = 38;
 
 // Multi-GPU exchange of demand vectors through peer memory.  Every rank owns
-// one XchgBuf (64 slots); rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
+// one XchgBuf (kXchgSlots slots); rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
 // rank's buffer (plain stores over NVLink), followed by flag = s + 1 with release.sys.
 constexpr int kMaxRanks = 8;
-constexpr int kXchgSlots = 64;
+constexpr int kXchgSlots = 256;  // 2.1 MB per rank; a rank's scans may run kXchgSlots / 2 steps ahead of its applies
 struct XchgRow {
     long long delta[2 * kMaxD];
     unsigned long long flag;  // step + 1 once delta[] is complete
@@ -69,6 +69,8 @@ struct XchgRow {
 };
 struct XchgBuf {
     XchgRow slot[kXchgSlots][kMaxRanks];
+    // start gate (egpu_peer_gate_dev): rank r stores its gate epoch into ready[r] of EVERY rank's buffer
+    unsigned long long ready[kMaxRanks];
 };
 struct PeerCfg {
     XchgBuf* buf[kMaxRanks];  // device-visible address of every rank's buffer ([rank] = own)
@@ -97,23 +99,47 @@ struct DevState {
         unsigned int ticket;
         unsigned int pad_[3];
     } epi[33];
+    // Multi-batch launches (egpu_bestfit_batches_dev): one slot per BATCH, taken from this ring in
+    // launch order; a launch group (see launch_multi) never holds more than half of it.
+    EpiSlot epi_multi[128];
+    unsigned long long gate_epoch;        // start gates passed so far (egpu_peer_gate_dev)
 };
 constexpr int kEpiSlots = 32;      // ring used by pipelined launches; slot 32 = accumulate-only launches
 constexpr int kPipeGroupMax = 24;  // at most this many launches between two fully ordered ones
+constexpr int kMultiSlots = 128;   // DevState::epi_multi
+constexpr int kMultiMax = 64;      // batches per multi-batch launch (descriptors travel as kernel parameters)
 
-// Lookup form of the sorted table, for large D (DESIGN.md §4.2).  With rows sorted by
+// One batch of a multi-batch launch: the arguments of egpu_bestfit_batch_dev, per batch.
+struct BatchDesc {
+    const int32_t* rc;
+    const int32_t* rm;
+    int32_t* idx;
+    long long* delta;     // int64[2*D] or nullptr
+    int32_t* table_out;   // int32[3*D] or nullptr
+    long long R;
+};
+struct MultiArgs {
+    BatchDesc b[kMultiMax];
+};
+static_assert(sizeof(MultiArgs) <= 3072, "descriptors + the scalar arguments must fit the 4 KB kernel-parameter space");
+
+// Lookup form of the sorted table, for large D (DESIGN.md §4.1b).  With rows sorted by
 // (fc, fm, d) the best fit of (c, m) is the first position j >= start[c] whose
 // fm_j >= m.  Let V be the distinct fm values in ascending order and rank(m) = #V < m;
 // then fm_j >= m  <=>  ridx_j >= rank(m)  (ridx_j = #V < fm_j), so the answer is a pure
-// table lookup  a[start[c]][rank(m)]  (device id, 0xFF = none).  rank(m) comes from a
-// bucket table over m >> 6: entry = (#V below the bucket) | (#V inside it) << 8.
+// table lookup  a2[c][rank(m)]  (device id, 0xFF = none; a2[c] = the row of position start[c]).
+// rank(m) comes from a bucket table over m >> 6.  Entry = lo << 8 | t:
+//   lo = #V below the bucket (0..64);  t = (threshold & 63) + 1 when exactly one value of V
+//   lies in the bucket, 64 when none (so  (m & 63) >= t  is  "threshold < m"), and bit 15 is
+//   set when several do (rare: the scan then walks v[] from lo).
 constexpr int kLutStride = kMaxD + 1;
 constexpr int kLutBuckets = (1 << 18 >> 6) + 1;  // last bucket: mem clamped to 2^18 = out of domain
+constexpr int kLutCRows = kCoreMax + 2;          // c = 0..100, and 101 = "core out of domain" (all 0xFF)
+constexpr uint32_t kLutMulti = 0x8000u;
 struct DevLut {
     uint16_t bucket[kLutBuckets + 7];
-    uint8_t a[kLutStride * kLutStride + 15];
-    uint32_t v[kMaxD];
-    uint8_t start[128];
+    uint8_t a2[kLutCRows * kLutStride + 10];
+    uint32_t v[kMaxD + 4];  // ascending distinct fm values, 0xFFFFFFFF past nv (sentinel for the walk)
     int32_t nv;
     int32_t pad_[3];
 };

@@ -1,11 +1,10 @@
 // egpu_plugin.cc — host logic between the kubelet device-plugin messages and the CUDA
 // best-fit scan: ID codec ("%d-%02d", pkg/plugins/gpushare.go:28,163) and
 // GetPreferredAllocation for one container (the stub at pkg/plugins/base.go:94-96).
-// Plain C++; the device choice is delegated to egpu_bestfit_batch (CUDA).
+// Plain C++; the device choice is delegated to egpu_bestfit_query (CUDA).
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -100,20 +99,17 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
         free_core[d] = resource == EGPU_RESOURCE_CORE ? (usable ? c : 0) : (usable ? EGPU_CORE_MAX : 0);
         free_mem[d] = resource == EGPU_RESOURCE_MEM ? (usable ? c : 0) : (usable ? EGPU_MEM_MAX : 0);
     }
-    // table_set + scan must not interleave with another preferred-allocation call on this
-    // context (each call installs its own table; use a context dedicated to these queries)
-    static std::mutex pair_mu;
-    std::lock_guard<std::mutex> pair_lock(pair_mu);
-    int rc = egpu_table_set(ctx, free_core.data(), free_mem.data(), D);
-    if (rc != EGPU_OK) return rc;
     // a request for 0 units of the constrained resource still needs 1 unit of the other
     // dimension on unusable GPUs to be excluded: unusable rows are (0, 0), request >= (0, 0)
     // would fit them, so ask for one unit of the unconstrained dimension
     int32_t req_core = resource == EGPU_RESOURCE_CORE ? allocation_size : 1;
     int32_t req_mem = resource == EGPU_RESOURCE_MEM ? allocation_size : 1;
     if (resource == EGPU_RESOURCE_CORE && allocation_size > EGPU_CORE_MAX) return EGPU_ERR_UNSAT;  // >100 core = several GPUs: not v1
+    // stateless query against this request's availability table: the context's own table (the
+    // node's committed placement) is neither read nor written, and the call
+    // holds the context mutex from the table upload to the answer
     int32_t idx = -1;
-    rc = egpu_bestfit_batch(ctx, &req_core, &req_mem, 1, &idx, nullptr, nullptr, 0);
+    int rc = egpu_bestfit_query(ctx, free_core.data(), free_mem.data(), D, &req_core, &req_mem, 1, &idx);
     if (rc != EGPU_OK) return rc;
     if (idx < 0) return EGPU_ERR_UNSAT;
     if (out_gpu) *out_gpu = idx;

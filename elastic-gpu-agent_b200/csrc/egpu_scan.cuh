@@ -112,6 +112,27 @@ __device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int
         static_cast<unsigned long long>(static_cast<uint32_t>(mem));
 }
 
+// Where a CTA's epilogue goes: the launch's (or, in a multi-batch launch, the batch's) slot of
+// running sums + arrival ticket, the exchange step to push under, and which of how many CTAs
+// of that batch this one is.
+struct EpiCtl {
+    DevState::EpiSlot* ep;
+    unsigned long long push;  // step + 1 when the demand vector must also go to the peers' exchange buffers, else 0
+    unsigned int lag;         // with push: also apply the exchanged vectors of step (step - lag) here
+    int tile, n_tiles;        // this CTA's number among the CTAs that share `ep`
+};
+// Single-batch launches carry it as one word: bits 0..7 = epilogue slot, bits 8..55 = step + 1
+// (0 = single GPU), bits 56..63 = lag; the CTAs of the grid are the tiles.
+__device__ __forceinline__ EpiCtl epi_from_word(DevState* st, unsigned long long slot_step) {
+    EpiCtl ec;
+    ec.ep = &st->epi[slot_step & 0xffu];
+    ec.push = (slot_step >> 8) & ((1ull << 48) - 1);
+    ec.lag = static_cast<unsigned int>(slot_step >> 56);
+    ec.tile = static_cast<int>(blockIdx.x);
+    ec.n_tiles = static_cast<int>(gridDim.x);
+    return ec;
+}
+
 // Second half of every snapshot epilogue.  `wacc` holds per-warp demand sums in shared
 // memory: core sum of device d of warp w at wacc[w * wstride + core_off + d], mem sum at
 // [... + mem_off + d].  Called by all threads after a __syncthreads().  Publishes the CTA's
@@ -121,15 +142,13 @@ template <int WARPS>
 __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
                                                  int32_t* sFc, int32_t* sFm, int32_t* sPosDev, int* sLast,
                                                  DevState* st, int D, long long* __restrict__ delta_out,
-                                                 int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                                                 int32_t* __restrict__ table_out, int flags, const EpiCtl& ec,
                                                  unsigned long long* __restrict__ tile_sums = nullptr) {
-    // slot_step: bits 0..7 = epilogue slot of this launch; bits 8.. = step + 1 when the demand
-    // vector must also be pushed to the peers' exchange buffers (0 = single GPU)
-    DevState::EpiSlot& ep = st->epi[slot_step & 0xffu];
-    const unsigned long long push = (slot_step >> 8) & ((1ull << 48) - 1);
-    // bits 56..63: with push, also apply the exchanged vectors of step (step - lag) here and
+    DevState::EpiSlot& ep = *ec.ep;
+    const unsigned long long push = ec.push;
+    // with push and lag: also apply the exchanged vectors of step (step - lag) here and
     // write ITS table' to table_out: no separate apply launches, no second stream
-    const unsigned long long lag = slot_step >> 56;
+    const unsigned long long lag = ec.lag;
     const int tid = threadIdx.x;
     if (tid < 2 * D) {
         const int j = tid < D ? core_off + tid : mem_off + (tid - D);
@@ -138,13 +157,13 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         for (int w = 0; w < WARPS; ++w) tot += wacc[w * wstride + j];
         if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
         // prefix-commit mode: this CTA owns a contiguous run of rows; keep its sums per device
-        if (tile_sums) tile_sums[static_cast<size_t>(blockIdx.x) * 2 * kMaxD + (tid < D ? tid : kMaxD + (tid - D))] = tot;
+        if (tile_sums) tile_sums[static_cast<size_t>(ec.tile) * 2 * kMaxD + (tid < D ? tid : kMaxD + (tid - D))] = tot;
         __threadfence();  // only the threads that published sums need to order them before the ticket
     }
     __syncthreads();
     if (tid == 0) {
         const unsigned int ticket = atomicAdd(&ep.ticket, 1u);
-        *sLast = (ticket == gridDim.x - 1);
+        *sLast = (ticket == static_cast<unsigned int>(ec.n_tiles - 1));
     }
     __syncthreads();
     if (!*sLast) return;
@@ -251,7 +270,7 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
 template <int DT, int THREADS>
 __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevState* st, int D,
                                                   long long* __restrict__ delta_out,
-                                                  int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                                                  int32_t* __restrict__ table_out, int flags, const EpiCtl& ec,
                                                   unsigned long long* __restrict__ tile_sums = nullptr) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -272,35 +291,28 @@ __device__ __forceinline__ void snapshot_epilogue(SnapSmem<DT, THREADS>& s, DevS
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&s.sWarpAcc[0][0], 2 * DT, 0, DT, s.sFc, s.sFm, s.sPosDev, &s.sLast, st, D, delta_out,
-                                   table_out, flags, slot_step, tile_sums);
+                                   table_out, flags, ec, tile_sums);
 }
 
-// CONTIG = false: vectors are dealt round-robin over the whole grid (the product mapping).
-// CONTIG = true (prefix-commit mode): CTA b scans the contiguous rows of "tile" b and leaves
-// its per-device sums in tile_sums[b][*]; everything else is the same kernel.
-template <int DT, int THREADS, bool CONTIG = false>
-__global__ void __launch_bounds__(THREADS)  // (forcing 5 CTAs/SM = 48 registers was measured slower: ptxas then puts
-                                            //  more of the adds on the ALU pipe; same-box A/B, DESIGN.md 7.2)
-bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
-                      const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
-                      unsigned long long* __restrict__ tile_sums) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+// The scan of one batch by one CTA: tile `tile` of `n_tiles` (in a single-batch launch the grid's
+// CTAs are the tiles; in a multi-batch launch every batch has its own run of tiles).
+// CONTIG = false: vectors are dealt round-robin over the batch's tiles (the product mapping).
+// CONTIG = true (prefix-commit mode): tile b scans the contiguous rows of "tile" b and the
+// epilogue leaves its per-device sums in tile_sums[b][*]; everything else is the same code.
+// Returns D.  Leaves the demand sums in s.hist; the caller runs snapshot_epilogue.
+template <int DT, int THREADS, bool CONTIG>
+__device__ __forceinline__ int sorted_scan_rows(SnapSmem<DT, THREADS>& s, DevState* __restrict__ st,
+                                                const int32_t* __restrict__ req_core, const int32_t* __restrict__ req_mem,
+                                                long long R, int32_t* __restrict__ out_idx, int tile_i, int n_tiles) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const bool late = (flags & kFlagLateWait) != 0;
-    const bool boundary = (flags & kFlagBoundary) != 0;
-    if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
-    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
-
     long long nvec = R >> 2;  // CONTIG: end of this CTA's tile
-    long long stride = static_cast<long long>(gridDim.x) * THREADS;
-    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+    long long stride = static_cast<long long>(n_tiles) * THREADS;
+    long long v = static_cast<long long>(tile_i) * THREADS + tid;
     if (CONTIG) {
-        const long long per = (nvec + gridDim.x - 1) / gridDim.x;
-        const long long lo = static_cast<long long>(blockIdx.x) * per;
+        const long long per = (nvec + n_tiles - 1) / n_tiles;
+        const long long lo = static_cast<long long>(tile_i) * per;
         nvec = (lo + per < nvec) ? lo + per : nvec;
         stride = THREADS;
         v = lo + tid;
@@ -369,16 +381,68 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
     // ragged tail: R % 4 rows, scalar (they are the LAST rows: in CONTIG mode they belong to the last tile)
-    if (blockIdx.x == (CONTIG ? gridDim.x - 1 : 0) && tid < static_cast<int>(R & 3)) {
+    if (tile_i == (CONTIG ? n_tiles - 1 : 0) && tid < static_cast<int>(R & 3)) {
         const long long r = ((R >> 2) << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
+    return D;
+}
+
+template <int DT, int THREADS, bool CONTIG = false>
+__global__ void __launch_bounds__(THREADS)  // (forcing 5 CTAs/SM = 48 registers was measured slower: ptxas then puts
+                                            //  more of the adds on the ALU pipe; same-box A/B, DESIGN.md 7.2)
+bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
+                      const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
+                      long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                      unsigned long long* __restrict__ tile_sums) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+    const bool late = (flags & kFlagLateWait) != 0;
+    const bool boundary = (flags & kFlagBoundary) != 0;
+    if (!late) pdl_wait();  // predecessor may have produced our inputs or changed the table
+    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
+    const int D = sorted_scan_rows<DT, THREADS, CONTIG>(s, st, req_core, req_mem, R, out_idx, static_cast<int>(blockIdx.x),
+                                                        static_cast<int>(gridDim.x));
     if (boundary) {  // everything older must be complete before the next group may start
         pdl_wait();
         pdl_trigger();
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step, CONTIG ? tile_sums : nullptr);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, epi_from_word(st, slot_step), CONTIG ? tile_sums : nullptr);
     if (late && !boundary) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
+}
+
+// Multi-batch launch (egpu_bestfit_batches_dev): K independent batches, all scored against the
+// same table, in ONE grid.  CTA (b, t) = tile t of batch b; every batch has its own epilogue
+// slot, so its last CTA publishes that batch's demand sums / table' (and pushes its exchange
+// step) as soon as that batch is done.  One launch latency, one ramp and one tail for K batches
+// instead of K: what the per-launch fixed cost (first DRAM touch, atomics, fence, ticket) was
+// eating at R = 1 M, and the launch floor at R = 1 k .. 100 k.
+template <int DT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+bestfit_sorted_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles, int flags,
+                            unsigned int slot_base, unsigned long long push_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
+    const bool late = (flags & kFlagLateWait) != 0;
+    const bool boundary = (flags & kFlagBoundary) != 0;
+    if (!late) pdl_wait();
+    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
+    const int batch = static_cast<int>(blockIdx.x) / tiles;
+    const int tile_i = static_cast<int>(blockIdx.x) - batch * tiles;
+    const BatchDesc& b = args.b[batch];
+    const int D = sorted_scan_rows<DT, THREADS, false>(s, st, b.rc, b.rm, b.R, b.idx, tile_i, tiles);
+    if (boundary) {
+        pdl_wait();
+        pdl_trigger();
+    }
+    EpiCtl ec;
+    ec.ep = &st->epi_multi[(slot_base + static_cast<unsigned int>(batch)) % kMultiSlots];
+    ec.push = push_base ? push_base + static_cast<unsigned long long>(batch) : 0ull;
+    ec.lag = 0;
+    ec.tile = tile_i;
+    ec.n_tiles = tiles;
+    snapshot_epilogue<DT, THREADS>(s, st, D, b.delta, b.table_out, flags, ec);
+    if (late && !boundary) pdl_wait();
 }
 
 // Packed wire format (include/egpu_alloc.h: egpu_bestfit_batch_packed): one uint32 per request
@@ -459,7 +523,7 @@ bestfit_sorted_packed_kernel(DevState* __restrict__ st, const uint32_t* __restri
     if (blockIdx.x == 0) {
         for (long long r = (nchunk << 9) + tid; r < R; r += THREADS) out_idx8[r] = static_cast<signed char>(decide(req[r]));
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, epi_from_word(st, slot_step));
     if (late) pdl_wait();
 }
 
@@ -518,7 +582,7 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
         const long long r = (nvec << 2) + tid;
         out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, slot_step);
+    snapshot_epilogue<DT, THREADS>(s, st, D, delta_out, table_out, flags, epi_from_word(st, slot_step));
 }
 
 // =============================================================================
@@ -526,22 +590,24 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
 // =============================================================================
 //
 // The register-resident scan above costs 3.5 instructions per (request, device) pair:
-// fine for D = 8 (HBM-bound), ALU-bound by 4x at D = 64.  The lookup form needs three
-// shared-memory reads and ~20 instructions per request whatever D is.
+// fine for D = 8 (HBM-bound), ALU-bound by 4x at D = 64.  The lookup form needs two
+// shared-memory reads and ~25 instructions per request whatever D is.
 
 // Builds DevLut from the sorted view in DevState.  One CTA; runs after every table change.
 __global__ void __launch_bounds__(256)
 lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
-    __shared__ uint32_t sFm[kMaxD], sFcs[kMaxD], sV[kMaxD];
+    __shared__ uint32_t sFm[kMaxD], sFcs[kMaxD], sV[kMaxD + 4];
     __shared__ int sFirst[kMaxD], sRidx[kMaxD], sNv;
+    __shared__ uint8_t sA[kLutStride * kLutStride];  // a[srow][rank]: first device at or after srow with ridx >= rank
+    __shared__ uint8_t sStart[kLutCRows];
     const int tid = threadIdx.x;
     const int D = st->D;
     if (tid < kMaxD) {
         const uint32_t k = tid < D ? st->sorted_k[tid] : 0u;
         sFm[tid] = (k >> 5) & 0x3FFFFu;
         sFcs[tid] = (k >> 24) & 0x7Fu;
-        sV[tid] = 0xFFFFFFFFu;
     }
+    if (tid < kMaxD + 4) sV[tid] = 0xFFFFFFFFu;
     __syncthreads();
     if (tid < D) {  // first occurrence of its fm value?
         int first = 1;
@@ -563,11 +629,11 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
     }
     __syncthreads();
     const int nv = sNv;
-    if (tid < kMaxD) lut->v[tid] = sV[tid];
-    if (tid < 128) {  // start[c] = first sorted position with fc >= c
+    if (tid < kMaxD + 4) lut->v[tid] = sV[tid];
+    if (tid < kLutCRows) {  // start[c] = first sorted position with fc >= c (c = 101: none, position D)
         int n = 0;
         for (int k = 0; k < D; ++k) n += (sFcs[k] < static_cast<uint32_t>(tid));
-        lut->start[tid] = static_cast<uint8_t>(n);
+        sStart[tid] = static_cast<uint8_t>(n);
     }
     if (tid < kLutStride) {  // column r of a[][]: walk the suffixes from the back
         const int r = tid;
@@ -575,8 +641,13 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
         for (int srow = kMaxD; srow >= 0; --srow) {
             if (srow < D && sRidx[srow] >= r) cur = static_cast<uint8_t>(st->sorted_dev[srow]);
             if (srow > D) cur = 0xFF;
-            lut->a[srow * kLutStride + r] = cur;
+            sA[srow * kLutStride + r] = cur;
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < kLutCRows * kLutStride; i += blockDim.x) {  // a2[c][r] = a[start[c]][r]
+        const int c = i / kLutStride, r = i - c * kLutStride;
+        lut->a2[i] = sA[sStart[c] * kLutStride + r];
     }
     for (int b = tid; b < kLutBuckets; b += blockDim.x) {
         const uint32_t lo_v = static_cast<uint32_t>(b) << 6, hi_v = lo_v + 64u;
@@ -585,63 +656,58 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
             lo += (sV[k] < lo_v);
             hi += (sV[k] < hi_v);
         }
-        lut->bucket[b] = static_cast<uint16_t>(lo | ((hi - lo) << 8));
+        const int n = hi - lo;
+        uint32_t e = static_cast<uint32_t>(lo) << 8;
+        if (n == 0) e |= 64u;
+        else if (n == 1) e |= (sV[lo] & 63u) + 1u;
+        else e |= kLutMulti | 64u;
+        lut->bucket[b] = static_cast<uint16_t>(e);
     }
 }
 
-// Demand sums of the lookup scan: lane-private like SnapSmem::hist, but SHARE lanes share
-// one accumulator (SHARE = 1, 2 or 4) and take turns, SHARE phases per update.  D = 64
-// with SHARE = 1 costs 16.6 KB per warp, which caps an SM at 8-12 warps; sharing trades
-// a few issue slots (the scan is nowhere near ALU-bound) for occupancy.
-template <int THREADS, int SHARE>
+// Demand sums of the lookup scan.  64-bit shared-memory adds compile to CAS loops on sm_100a
+// (ATOMS.CAST.SPIN.64), lane-private 64-bit sums cost 16.6 KB per warp; what is used instead
+// is native 32-bit ATOMS.ADD on small per-warp tables, folded into 64-bit sums before a word
+// could overflow.
+//   ACC = 0  one table per warp, three words per device (core, mem & 0xffff, mem >> 16 - the
+//            last only when non-zero), infeasible rows issue nothing (two branch regions per
+//            request); fold every 128 trips.  Round 1's form, kept for A/B (EGPU_LUT_ACC=atomic3).
+//   ACC = 1  two UNCONDITIONAL adds per request - word 0 = core | (mem >> 16) << 20, word 1 =
+//            mem & 0xffff - into one of 8 copies of the table per warp (copy = lane / 4; the
+//            copies are 140 words apart, i.e. rotated by 12 banks, so the hot devices of a batch
+//            spread over the banks), infeasible rows into a per-lane dummy word: no branches,
+//            no shared hot spot.  A copy receives 4 lanes x 8 rows per trip, so word 0's 12-bit
+//            mem >> 16 field (<= 3 per add) lasts 42 trips: fold every 32.
+constexpr int kLutFlushTrips3 = 128;  // ACC 0: x 8 rows per thread per trip x 32 lanes = 32 K rows per warp
+constexpr int kLutFlushTrips2 = 32;   // ACC 1
+constexpr int kLutCopies = 8;
+constexpr int kLutPlane = kMaxD + 4;                 // 64 devices + one dummy word per lane of the copy
+constexpr int kLutCopyStride = 2 * kLutPlane + 4;    // 140 words = 12 banks
+template <int THREADS, int ACC>
 struct LutSmem {
     DevLut lut;
     unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
     int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     int sLast;
-    alignas(16) unsigned long long hist[THREADS / 32][kMaxD + 1][32 / SHARE];  // zeroed with 128-bit stores
+    alignas(16) uint32_t hist32[THREADS / 32][ACC == 0 ? 3 * kMaxD : kLutCopies * kLutCopyStride];
 };
 
-// Alternative demand sums (ATOMIC = true): one small table per warp, updated with native 32-bit
-// shared-memory atomics (ATOMS.ADD; a 64-bit shared add is a CAS loop on sm_100a).  Three words
-// per device - core, mem & 0xffff, mem >> 16 - so that a warp can add 32 K rows before a word
-// could overflow; the words are folded into the 64-bit sWarpAcc every kLutFlushTrips trips.
-constexpr int kLutFlushTrips = 128;  // x 8 rows per thread per trip x 32 lanes = 32 K rows per warp
-template <int THREADS>
-struct LutSmemAtomic {
-    DevLut lut;
-    unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
-    int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
-    int sLast;
-    alignas(16) uint32_t hist32[THREADS / 32][3][kMaxD];
-};
-
-template <int THREADS, int SHARE, bool CONTIG = false, bool ATOMIC = false>
-__global__ void __launch_bounds__(THREADS)
-bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
-                   const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
-                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
-                   const DevLut* __restrict__ glut, unsigned long long* __restrict__ tile_sums) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Smem = typename std::conditional<ATOMIC, LutSmemAtomic<THREADS>, LutSmem<THREADS, SHARE>>::type;
-    auto& sm = *reinterpret_cast<Smem*>(smem_raw);
-    constexpr int LW = 32 / SHARE;  // accumulator columns per warp
+// The lookup scan of one batch by one CTA (tile `tile_i` of `n_tiles`, as sorted_scan_rows).
+// Leaves the warp sums in sm.sWarpAcc; the caller synchronises and runs epilogue_publish.
+template <int THREADS, bool CONTIG, int ACC>
+__device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState* __restrict__ st,
+                                             const int32_t* __restrict__ req_core, const int32_t* __restrict__ req_mem,
+                                             long long R, int32_t* __restrict__ out_idx, const DevLut* __restrict__ glut,
+                                             int tile_i, int n_tiles) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int col = lane & (LW - 1);
-    const int phase = lane / LW;
-    const bool late = (flags & kFlagLateWait) != 0;
-    const bool boundary = (flags & kFlagBoundary) != 0;
-    if (!late) pdl_wait();
-    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
-
     long long nvec = R >> 2;
-    long long stride = static_cast<long long>(gridDim.x) * THREADS;
-    long long v = static_cast<long long>(blockIdx.x) * THREADS + tid;
+    long long stride = static_cast<long long>(n_tiles) * THREADS;
+    long long v = static_cast<long long>(tile_i) * THREADS + tid;
     if (CONTIG) {
-        const long long per = (nvec + gridDim.x - 1) / gridDim.x;
-        const long long lo = static_cast<long long>(blockIdx.x) * per;
+        const long long per = (nvec + n_tiles - 1) / n_tiles;
+        const long long lo = static_cast<long long>(tile_i) * per;
         nvec = (lo + per < nvec) ? lo + per : nvec;
         stride = THREADS;
         v = lo + tid;
@@ -656,119 +722,102 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
         c1 = ld_stream_v4(req_core + 4 * (v + stride));
         m1 = ld_stream_v4(req_mem + 4 * (v + stride));
     }
-    // shared-memory tile of the lookup tables (12.8 KB, L2-resident source)
+    // shared-memory tile of the lookup tables (15 KB, L2-resident source)
     {
         const uint4* src = reinterpret_cast<const uint4*>(glut);
         uint4* dst = reinterpret_cast<uint4*>(&sm.lut);
         for (int i = tid; i < static_cast<int>(sizeof(DevLut) / 16); i += THREADS) dst[i] = src[i];
     }
     const int D = st->D;
-    if constexpr (ATOMIC) {
-        uint4* hz = reinterpret_cast<uint4*>(&sm.hist32[warp][0][0]);
-        constexpr int n16 = 3 * kMaxD * 4 / 16;
-        for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int j = lane; j < 2 * kMaxD; j += 32) sm.sWarpAcc[warp][j] = 0ull;
-    } else {  // zero this warp's accumulators with 128-bit stores
-        uint4* hz = reinterpret_cast<uint4*>(&sm.hist[warp][0][0]);
-        constexpr int n16 = (kMaxD + 1) * LW * 8 / 16;
+    {  // zero this warp's 32-bit tables
+        uint4* hz = reinterpret_cast<uint4*>(&sm.hist32[warp][0]);
+        constexpr int n16 = static_cast<int>(sizeof(sm.hist32[0]) / 16);
         for (int i = lane; i < n16; i += 32) hz[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    // 64-bit running sums of this warp: lane L keeps devices L and L + 32
+    unsigned long long acc_c[2] = {0ull, 0ull}, acc_m[2] = {0ull, 0ull};
     __syncthreads();
     const DevLut& L = sm.lut;
+    uint32_t* const hw = &sm.hist32[warp][0];
+    uint32_t* const hcopy = hw + (ACC == 1 ? (lane >> 2) * kLutCopyStride : 0);
+    const uint32_t dummy_col = static_cast<uint32_t>(kMaxD) + (static_cast<uint32_t>(lane) & 3u);
 
-    // lookups for one request: no data-dependent loop on the common path
-    auto lookup = [&](int32_t core, int32_t mem) -> int32_t {
-        const uint32_t c = min(static_cast<uint32_t>(core), 127u);
+    // device (0..63) or 0xFF for one request: two dependent shared-memory reads on the common path
+    auto lookup = [&](int32_t core, int32_t mem) -> uint32_t {
+        const uint32_t c = min(static_cast<uint32_t>(core), static_cast<uint32_t>(kCoreMax + 1));
         const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
-        const uint32_t srow = L.start[c];
         const uint32_t e = L.bucket[m >> 6];
-        const uint32_t lo = e & 0xffu, n = e >> 8;
-        uint32_t rank = lo + ((n != 0u) & (L.v[lo & 63u] < m));
-        for (uint32_t i = 1; i < n; ++i) rank += (L.v[lo + i] < m);  // rare: several distinct fm in one 64 MiB bucket
-        return static_cast<int32_t>(static_cast<int8_t>(L.a[srow * kLutStride + rank]));
-    };
-    // Demand sums for the four requests of one vector at once.  Requests of this thread that
-    // chose the same device are merged first (the later one is redirected to the dummy row
-    // with nothing to add), so the four read-modify-writes are independent and can be issued
-    // as four loads, four adds, four stores per phase instead of four dependent chains.
-    // ATOMIC: fold this warp's 32-bit words into its 64-bit sums and clear them
-    auto flush32 = [&]() {
-        if constexpr (ATOMIC) {
-            __syncwarp();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int d = lane + 32 * half;
-                const uint32_t hc = sm.hist32[warp][0][d], hl = sm.hist32[warp][1][d], hh = sm.hist32[warp][2][d];
-                sm.hist32[warp][0][d] = 0u;
-                sm.hist32[warp][1][d] = 0u;
-                sm.hist32[warp][2][d] = 0u;
-                sm.sWarpAcc[warp][d] += hc;
-                sm.sWarpAcc[warp][kMaxD + d] += static_cast<unsigned long long>(hl) + (static_cast<unsigned long long>(hh) << 16);
-            }
-            __syncwarp();
-        }
-    };
-    auto accumulate4 = [&](const int4& r, const int4& c, const int4& m) {
-        if constexpr (ATOMIC) {
-            // (Measured and rejected: merging a thread's same-device requests first, 3.24 vs 3.17 us;
-            // predicated red.shared in inline PTX - ptxas gives every one its own BSSY/BRA/BSYNC.)
-            auto add1 = [&](int32_t i, int32_t core, int32_t mem) {
-                if (i >= 0) {  // feasible rows are inside the domain: core <= 100, mem < 2^18
-                    atomicAdd(&sm.hist32[warp][0][i], static_cast<uint32_t>(core));
-                    atomicAdd(&sm.hist32[warp][1][i], static_cast<uint32_t>(mem) & 0xffffu);
-                    if (mem >> 16) atomicAdd(&sm.hist32[warp][2][i], static_cast<uint32_t>(mem) >> 16);
-                }
-            };
-            add1(r.x, c.x, m.x);
-            add1(r.y, c.y, m.y);
-            add1(r.z, c.z, m.z);
-            add1(r.w, c.w, m.w);
+        uint32_t rank = (e >> 8) & 0x7Fu;
+        if (e & kLutMulti) {  // rare: several distinct fm values inside one 64 MiB bucket
+            while (L.v[rank] < m) ++rank;
         } else {
-        auto val = [](int32_t core, int32_t mem) {
-            return (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-                   static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-        };
-        int32_t i0 = r.x, i1 = r.y, i2 = r.z, i3 = r.w;
-        unsigned long long v0 = val(c.x, m.x), v1 = val(c.y, m.y), v2 = val(c.z, m.z), v3 = val(c.w, m.w);
-        if (i0 < 0) v0 = 0;  // infeasible rows carry out-of-domain values: keep the dummy row harmless
-        if (i1 < 0) v1 = 0;
-        if (i2 < 0) v2 = 0;
-        if (i3 < 0) v3 = 0;
-        if (i3 == i2) { v2 += v3; v3 = 0; i3 = -1; }
-        if (i3 == i1) { v1 += v3; v3 = 0; i3 = -1; }
-        if (i3 == i0) { v0 += v3; v3 = 0; i3 = -1; }
-        if (i2 == i1) { v1 += v2; v2 = 0; i2 = -1; }
-        if (i2 == i0) { v0 += v2; v2 = 0; i2 = -1; }
-        if (i1 == i0) { v0 += v1; v1 = 0; i1 = -1; }
-        unsigned long long* h0 = &sm.hist[warp][i0 + 1][col];
-        unsigned long long* h1 = &sm.hist[warp][i1 + 1][col];
-        unsigned long long* h2 = &sm.hist[warp][i2 + 1][col];
-        unsigned long long* h3 = &sm.hist[warp][i3 + 1][col];
-#pragma unroll
-        for (int p = 0; p < SHARE; ++p) {
-            if (SHARE == 1 || phase == p) {
-                const unsigned long long a0 = *h0, a1 = *h1, a2 = *h2, a3 = *h3;
-                *h0 = a0 + v0;
-                *h1 = a1 + v1;
-                *h2 = a2 + v2;
-                *h3 = a3 + v3;  // several redirected requests may all hit the dummy row: its content is never read
-            }
-            if (SHARE > 1) __syncwarp();
+            rank += ((m & 63u) >= (e & 0x7Fu)) ? 1u : 0u;
         }
-        }  // !ATOMIC
+        return L.a2[c * kLutStride + rank];
+    };
+    // fold this warp's 32-bit words into the 64-bit sums and clear them
+    auto flush32 = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int d = lane + 32 * half;
+            if constexpr (ACC == 0) {
+                const uint32_t hc = hw[d], hl = hw[kMaxD + d], hh = hw[2 * kMaxD + d];
+                hw[d] = 0u;
+                hw[kMaxD + d] = 0u;
+                hw[2 * kMaxD + d] = 0u;
+                acc_c[half] += hc;
+                acc_m[half] += static_cast<unsigned long long>(hl) + (static_cast<unsigned long long>(hh) << 16);
+            } else {
+                uint32_t cs = 0, mh = 0, ml = 0;
+#pragma unroll
+                for (int j = 0; j < kLutCopies; ++j) {  // bank = (12 j + lane) mod 32: conflict-free
+                    uint32_t* h = hw + j * kLutCopyStride;
+                    const uint32_t w0 = h[d], w1 = h[kLutPlane + d];
+                    h[d] = 0u;
+                    h[kLutPlane + d] = 0u;
+                    cs += w0 & 0xFFFFFu;
+                    mh += w0 >> 20;
+                    ml += w1;
+                }
+                acc_c[half] += cs;
+                acc_m[half] += static_cast<unsigned long long>(ml) + (static_cast<unsigned long long>(mh) << 16);
+            }
+        }
+        __syncwarp();
+    };
+    auto add1 = [&](uint32_t dev, int32_t core, int32_t mem) {
+        if constexpr (ACC == 0) {
+            if (dev < static_cast<uint32_t>(kMaxD)) {  // feasible rows are inside the domain: core <= 100, mem < 2^18
+                atomicAdd(&hw[dev], static_cast<uint32_t>(core));
+                atomicAdd(&hw[kMaxD + dev], static_cast<uint32_t>(mem) & 0xffffu);
+                if (mem >> 16) atomicAdd(&hw[2 * kMaxD + dev], static_cast<uint32_t>(mem) >> 16);
+            }
+        } else {
+            // infeasible rows (0xFF) go to this lane's dummy word, whose content is never read
+            // (their core / mem may be anything: nothing carries from one word into another)
+            const uint32_t col = min(dev, dummy_col);
+            atomicAdd(&hcopy[col], static_cast<uint32_t>(core) | ((static_cast<uint32_t>(mem) >> 16) << 20));
+            atomicAdd(&hcopy[kLutPlane + col], static_cast<uint32_t>(mem) & 0xffffu);
+        }
+    };
+    auto decide = [&](int32_t core, int32_t mem) -> int32_t {
+        const uint32_t dev = lookup(core, mem);
+        add1(dev, core, mem);
+        return static_cast<int32_t>(static_cast<int8_t>(dev));
     };
     auto decide4 = [&](const int4& c, const int4& m) -> int4 {
         int4 r;
-        r.x = lookup(c.x, m.x);
-        r.y = lookup(c.y, m.y);
-        r.z = lookup(c.z, m.z);
-        r.w = lookup(c.w, m.w);
-        accumulate4(r, c, m);
+        r.x = decide(c.x, m.x);
+        r.y = decide(c.y, m.y);
+        r.z = decide(c.z, m.z);
+        r.w = decide(c.w, m.w);
         return r;
     };
+    constexpr int kFlushTrips = ACC == 0 ? kLutFlushTrips3 : kLutFlushTrips2;
     int trips = 0;
-    while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: accumulate() synchronises the warp
-        if (ATOMIC && ++trips == kLutFlushTrips) {
+    while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: flush32() synchronises the warp
+        if (++trips == kFlushTrips) {
             flush32();
             trips = 0;
         }
@@ -783,55 +832,78 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
             nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
             nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
         }
-        // lanes past the end carry core = mem = -1: infeasible, lands in the dummy row
-        if (!has0) { c0 = make_int4(-1, -1, -1, -1); m0 = c0; }
-        if (!has1) { c1 = make_int4(-1, -1, -1, -1); m1 = c1; }
-        const int4 r0 = decide4(c0, m0);
-        const int4 r1 = decide4(c1, m1);
-        if (has0) st_stream_v4(out_idx + 4 * v, r0);
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), r1);
+        if (has0) st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
+        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
         v = vn;
         has0 = nhas0;
         has1 = nhas1;
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
-    if (blockIdx.x == (CONTIG ? gridDim.x - 1 : 0) && warp == 0) {  // ragged tail: R % 4 rows (the last ones)
-        const bool mine = lane < static_cast<int>(R & 3);
-        const long long r = ((R >> 2) << 2) + lane;
-        const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
-        const int32_t idx = lookup(c, m);
-        accumulate4(make_int4(idx, -1, -1, -1), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0));
-        if (mine) out_idx[r] = idx;
+    if (tile_i == (CONTIG ? n_tiles - 1 : 0) && tid < static_cast<int>(R & 3)) {  // ragged tail: R % 4 rows (the last ones)
+        const long long r = ((R >> 2) << 2) + tid;
+        out_idx[r] = decide(req_core[r], req_mem[r]);
     }
-    // warp sums -> sWarpAcc, transposed: lane L adds up the LW columns of devices L and L + 32
-    // (rotated start column: conflict-free), instead of three warp reductions per device
-    __syncwarp();
-    if constexpr (ATOMIC) {
-        flush32();
-    } else {
+    flush32();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int d = lane + 32 * half;
-            unsigned long long sc = 0, smem_sum = 0;
-            if (d < D) {
-#pragma unroll 4
-                for (int k = 0; k < LW; ++k) {
-                    const unsigned long long hv = sm.hist[warp][d + 1][(k + lane) & (LW - 1)];
-                    sc += hv >> kAccShift;
-                    smem_sum += hv & ((1ull << kAccShift) - 1ull);
-                }
-            }
-            sm.sWarpAcc[warp][d] = sc;
-            sm.sWarpAcc[warp][kMaxD + d] = smem_sum;
-        }
+    for (int half = 0; half < 2; ++half) {
+        sm.sWarpAcc[warp][lane + 32 * half] = acc_c[half];
+        sm.sWarpAcc[warp][kMaxD + lane + 32 * half] = acc_m[half];
     }
+    return D;
+}
+
+template <int THREADS, bool CONTIG = false, int ACC = 1>
+__global__ void __launch_bounds__(THREADS)
+bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
+                   const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
+                   long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
+                   const DevLut* __restrict__ glut, unsigned long long* __restrict__ tile_sums) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& sm = *reinterpret_cast<LutSmem<THREADS, ACC>*>(smem_raw);
+    const bool late = (flags & kFlagLateWait) != 0;
+    const bool boundary = (flags & kFlagBoundary) != 0;
+    if (!late) pdl_wait();
+    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
+    const int D = lut_scan_rows<THREADS, CONTIG, ACC>(sm, st, req_core, req_mem, R, out_idx, glut, static_cast<int>(blockIdx.x),
+                                                      static_cast<int>(gridDim.x));
     if (boundary) {
         pdl_wait();
         pdl_trigger();
     }
     __syncthreads();
     epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
-                                   delta_out, table_out, flags, slot_step, CONTIG ? tile_sums : nullptr);
+                                   delta_out, table_out, flags, epi_from_word(st, slot_step), CONTIG ? tile_sums : nullptr);
+    if (late && !boundary) pdl_wait();
+}
+
+// Multi-batch form of the lookup scan (see bestfit_sorted_multi_kernel).
+template <int THREADS, int ACC>
+__global__ void __launch_bounds__(THREADS)
+bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles, int flags,
+                         unsigned int slot_base, unsigned long long push_base, const DevLut* __restrict__ glut) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    auto& sm = *reinterpret_cast<LutSmem<THREADS, ACC>*>(smem_raw);
+    const bool late = (flags & kFlagLateWait) != 0;
+    const bool boundary = (flags & kFlagBoundary) != 0;
+    if (!late) pdl_wait();
+    if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
+    const int batch = static_cast<int>(blockIdx.x) / tiles;
+    const int tile_i = static_cast<int>(blockIdx.x) - batch * tiles;
+    const BatchDesc& b = args.b[batch];
+    const int D = lut_scan_rows<THREADS, false, ACC>(sm, st, b.rc, b.rm, b.R, b.idx, glut, tile_i, tiles);
+    if (boundary) {
+        pdl_wait();
+        pdl_trigger();
+    }
+    __syncthreads();
+    EpiCtl ec;
+    ec.ep = &st->epi_multi[(slot_base + static_cast<unsigned int>(batch)) % kMultiSlots];
+    ec.push = push_base ? push_base + static_cast<unsigned long long>(batch) : 0ull;
+    ec.lag = 0;
+    ec.tile = tile_i;
+    ec.n_tiles = tiles;
+    epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
+                                   b.delta, b.table_out, flags, ec);
     if (late && !boundary) pdl_wait();
 }
 
@@ -872,9 +944,53 @@ apply_deltas_kernel(DevState* __restrict__ st, const long long* __restrict__ del
 // Multi-GPU step 2, peer-memory form: wait until every rank's demand vector of `step` has
 // landed in THIS rank's exchange buffer, then apply their sum.  One CTA.  The spin gives up
 // after ~2 s (a rank died): DevState::peer_timeout records it and the table is left alone.
+constexpr int kApplyMax = 64;  // steps one apply launch may cover
 struct ApplyOuts {
-    int32_t* table_out[8];
+    int32_t* table_out[kApplyMax];
 };
+
+// Start gate of a sharded sequence (egpu_peer_gate_dev).  One thread block.  Waits until THIS
+// rank's host has opened the gate (egpu_peer_gate_open: the host has finished enqueueing what
+// follows the gate on the stream), then tells every peer and waits until every peer has said the
+// same.  What follows the gate on the stream therefore starts within a peer-flag latency of the
+// same instant on every rank, and nothing after it waits for a host.  Epochs count up from 1;
+// a rank can be at most one gate ahead of a peer, so ">= epoch" is the arrival test.  Gives up
+// after ~2 s (peer_timeout = ~0).
+__global__ void __launch_bounds__(32)
+gate_kernel(DevState* __restrict__ st, const unsigned long long* __restrict__ host_open) {
+    const int world = st->peer.world, me = st->peer.rank;
+    const int lane = threadIdx.x;
+    const unsigned long long epoch = st->gate_epoch + 1;
+    const long long t0 = clock64();
+    bool ok = true;
+    if (lane == 0) {
+        for (;;) {
+            unsigned long long h;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(h) : "l"(host_open) : "memory");
+            if (h >= epoch) break;
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    if (lane < world) {
+        unsigned long long* f = &st->peer.buf[lane]->ready[me];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        const unsigned long long* mine = &st->peer.buf[me]->ready[lane];
+        for (;;) {
+            unsigned long long r;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(r) : "l"(mine) : "memory");
+            if (r >= epoch) break;
+            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            __nanosleep(100);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        st->gate_epoch = epoch;
+        if (!ok) st->peer_timeout = ~0ull;
+    }
+}
 
 __global__ void __launch_bounds__(kMaxD)
 apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus1, int nsteps, ApplyOuts outs, int commit) {
@@ -1062,7 +1178,8 @@ prefix_cut_kernel(const DevState* __restrict__ st, const int32_t* __restrict__ i
     // (2) rows of the cut tile, in order
     const long long nvec = R >> 2;
     const long long per = (nvec + n_tiles - 1) / n_tiles;
-    const long long row_lo = cut_tile * per * 4;
+    long long row_lo = cut_tile * per * 4;
+    if (row_lo > nvec * 4) row_lo = nvec * 4;  // capped grids: ceil(nvec / n_tiles) can leave the last tile only the ragged tail
     long long row_hi = (cut_tile + 1) * per * 4;
     if (row_hi > nvec * 4) row_hi = nvec * 4;
     if (cut_tile == n_tiles - 1) row_hi = R;  // the ragged tail belongs to the last tile

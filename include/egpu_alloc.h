@@ -202,6 +202,37 @@ int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                            int32_t* d_out_idx, int64_t* d_delta,
                            int32_t* d_table_out, int flags, void* stream);
 
+/* Several batches in ONE launch.  Every batch is what egpu_bestfit_batch_dev takes - its own
+ * request arrays, index array, d_delta (may be NULL) and d_table_out (may be NULL) - and all K
+ * (1..EGPU_MAX_BATCHES) are scored against the current table, so the result of each batch is
+ * exactly what K separate non-committing calls would produce; only the launch latency, ramp and
+ * tail are paid once instead of K times (at R = 1 M that fixed cost is about a third of a lone
+ * launch; at R <= 100 k it is nearly all of it).  Asynchronous on `stream`.  flags:
+ * EGPU_F_INPUTS_READY only (a multi-batch launch never commits: install a table' with
+ * egpu_table_set or a committing single-batch call).  Outputs of different batches must not
+ * overlap (EGPU_ERR_INVALID).  Batches may have different R (R = 0 allowed). */
+#define EGPU_MAX_BATCHES 64
+typedef struct egpu_batch {
+    const int32_t* d_req_core;
+    const int32_t* d_req_mem;
+    int64_t        R;
+    int32_t*       d_out_idx;
+    int64_t*       d_delta;      /* int64[2*D] or NULL */
+    int32_t*       d_table_out;  /* int32[3*D] or NULL */
+} egpu_batch;
+int egpu_bestfit_batches_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags,
+                             void* stream);
+
+/* Stateless query: scores R requests against the table GIVEN HERE (free_core/free_mem[D], host
+ * arrays, same domain as egpu_table_set) and returns the indices.  The context's own table,
+ * its oversubscription flags and lookup tables are not read or written, so a context that
+ * tracks the node's committed placement can also answer GetPreferredAllocation-style
+ * what-if questions (egpu_preferred_allocation uses this).  Host buffers; returns when out_idx
+ * is valid. */
+int egpu_bestfit_query(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D,
+                       const int32_t* req_core, const int32_t* req_mem, int64_t R,
+                       int32_t* out_idx);
+
 /* Multi-GPU step 2: after the G per-rank delta vectors (int64[G][2*D], rank
  * major) have been all-gathered, subtract their sum from the current table on
  * this rank: d_table_out (may be NULL) receives int32[3*D] as above, and with
@@ -222,8 +253,8 @@ int egpu_table_apply_deltas_dev(egpu_ctx* ctx, const int64_t* d_deltas, int G,
  *   egpu_table_apply_peers_dev    waits (acquire) until all `world` vectors of `step`
  *       have landed locally, applies their sum: table' (and commit) as in snapshot mode.
  * `step` must increase by one per sharded step on every rank; a rank's scans may run at
- * most 32 steps ahead of its own applies (64 exchange slots: then no peer can be more than
- * 63 steps ahead of what this rank has consumed).  The scan itself never commits. */
+ * most 128 steps ahead of its own applies (256 exchange slots: then no peer can be more than
+ * 255 steps ahead of what this rank has consumed).  The scan itself never commits. */
 #define EGPU_IPC_HANDLE_BYTES 64
 #define EGPU_MAX_RANKS 8
 int egpu_peer_export(egpu_ctx* ctx, void* handle_out);
@@ -235,6 +266,21 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                                  uint64_t step, void* stream);
 int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out,
                                int commit, void* stream);
+/* K sharded steps in one launch: batch k is exchange step first_step + k (egpu_bestfit_batches_dev
+ * + the fused push of egpu_bestfit_batch_shard_dev); d_table_out of the batches is ignored
+ * (table' comes from the apply calls). */
+int egpu_bestfit_batches_shard_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags,
+                                   uint64_t first_step, void* stream);
+/* Start gate for a sharded sequence.  egpu_peer_gate_dev enqueues a one-warp kernel that
+ * waits (i) for this rank's host to call egpu_peer_gate_open - which the caller does after it
+ * has enqueued everything that follows the gate - and (ii) for every peer's gate to have
+ * reached the same point, through flags in peer memory.  The work behind the gate then starts
+ * at the same time on every rank without any host in the way: launch skew between the ranks'
+ * host threads no longer lands inside the sequence.  Every gate_dev needs exactly one
+ * gate_open, on every rank, in the same order.  Works unattached too (host part only).
+ * Gives up after ~2 s (egpu_peer_last_timeout returns -1). */
+int egpu_peer_gate_dev(egpu_ctx* ctx, void* stream);
+int egpu_peer_gate_open(egpu_ctx* ctx);
 /* Prefix-commit (EGPU_F_PREFIX_COMMIT semantics, see egpu_bestfit_batch) over row shards.
  * The batch is the concatenation of the ranks' shards in rank order; request r of rank g
  * commits iff the running demand of its device over ALL earlier rows - the whole shards of
@@ -264,7 +310,7 @@ int egpu_bestfit_batch_shard_lag_dev(egpu_ctx* ctx, const int32_t* d_req_core,
                                      int32_t* d_out_idx, int64_t* d_delta, int flags,
                                      uint64_t step, int lag, int32_t* d_table_out_lagged,
                                      void* stream);
-/* Same for nsteps (1..8) consecutive steps in one launch; d_table_outs is a HOST array of
+/* Same for nsteps (1..64) consecutive steps in one launch; d_table_outs is a HOST array of
  * nsteps device pointers (entries may be NULL).  With commit the steps are applied on top
  * of each other and the last table' is installed. */
 int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nsteps,

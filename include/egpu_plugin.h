@@ -12,7 +12,7 @@
  *       api.proto:133-150), the body baseDevicePlugin.GetPreferredAllocation leaves empty
  *       (pkg/plugins/base.go:94-96).
  *
- * The choice itself is made by the CUDA best-fit scan (egpu_bestfit_batch); this file
+ * The choice itself is made by the CUDA best-fit scan (egpu_bestfit_query); this file
  * only turns ID strings into the capacity table and the answer back into IDs.  No CPU
  * fallback: without a context (no GPU) the call fails.
  */
@@ -48,7 +48,10 @@ int egpu_device_id_parse(const char* id, int32_t* gpu, int64_t* unit);
  * Output: out_positions[allocation_size] = indices into available_ids of the chosen IDs,
  * must-include IDs first, then the lowest unit numbers of the chosen GPU; *out_gpu = the
  * GPU index.  EGPU_ERR_UNSAT when no single GPU can satisfy the request (kubelet then
- * falls back to its own choice), EGPU_ERR_PARSE on a malformed ID. */
+ * falls back to its own choice), EGPU_ERR_PARSE on a malformed ID.
+ * The context's own capacity table is not touched (the availability table of the request is
+ * scored through egpu_bestfit_query), so the context that tracks the node's committed
+ * placement can serve these calls too, concurrently with commits and replays. */
 int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, int64_t n_available,
                               const char* const* must_include_ids, int64_t n_must,
                               int32_t allocation_size, int resource, int32_t* out_positions,

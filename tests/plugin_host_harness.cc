@@ -1,6 +1,6 @@
 // Test harness (CPU): links elastic-gpu-agent_b200/csrc/egpu_plugin.cc - the host logic of
-// GetPreferredAllocation - against RECORDING stand-ins for the two device entry points it uses,
-// egpu_table_set and egpu_bestfit_batch.  The stand-in for the scan computes nothing: it hands
+// GetPreferredAllocation - against a RECORDING stand-in for the device entry point it uses,
+// egpu_bestfit_query.  The stand-in for the scan computes nothing: it hands
 // back the answer the test scripted (which the test takes from the oracle) and records what it
 // was asked.  Built by tests/test_plugin_host_cpu.py.
 #include <cstdint>
@@ -16,16 +16,12 @@ int g_sets = 0, g_scans = 0;
 
 extern "C" {
 
-int egpu_table_set(egpu_ctx*, const int32_t* free_core, const int32_t* free_mem, int32_t D) {
+int egpu_bestfit_query(egpu_ctx*, const int32_t* free_core, const int32_t* free_mem, int32_t D, const int32_t* req_core,
+                       const int32_t* req_mem, int64_t R, int32_t* out_idx) {
+    if (R != 1) return EGPU_ERR_INVALID;
     g_fc.assign(free_core, free_core + D);
     g_fm.assign(free_mem, free_mem + D);
     g_sets += 1;
-    return EGPU_OK;
-}
-
-int egpu_bestfit_batch(egpu_ctx*, const int32_t* req_core, const int32_t* req_mem, int64_t R, int32_t* out_idx, int64_t*,
-                       int64_t*, int) {
-    if (R != 1) return EGPU_ERR_INVALID;
     g_req_core = req_core[0];
     g_req_mem = req_mem[0];
     g_scans += 1;

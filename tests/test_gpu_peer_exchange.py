@@ -167,6 +167,88 @@ def test_world2_two_processes_one_gpu(lag, oracle_c, egpu):
         assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
 
 
+def _multi_rank_main(rank, world, conn, peer_conn, K, R, replays):
+    """cfg4 (D = 64) row-sharded: every replay is gate -> one multi-batch launch of K sharded steps
+    -> apply launches on a second stream, the shape bench.py --gpus N captures in a CUDA graph."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import elastic_gpu_agent_b200 as e
+    torch.cuda.set_device(0)
+    w = e.synth.workload("cfg4")
+    D = 64
+    a = e.BestFitAllocator(0)
+    a.set_table(w["free_core"], w["free_mem"])
+    mine = a.peer_export()
+    peer_conn.send(mine)
+    other = peer_conn.recv()
+    a.peer_attach(rank, world, [mine, other] if rank == 0 else [other, mine])
+    peer_conn.send("attached")
+    assert peer_conn.recv() == "attached"
+    st, ap = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        tens, tup = [], []
+        for k in range(K):
+            rc, rm = e.synth.requests(4, 40 + k, R, first_row=rank * R)
+            c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
+            idx = torch.empty(R, dtype=torch.int32, device="cuda")
+            dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+            tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+            tens.append((c, m, idx, dl, tab))
+            tup.append((c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), 0))
+    torch.cuda.synchronize()
+    batches = a.make_batches(tup)
+    for rep in range(replays):
+        # step numbers restart at 0 on every replay (as a replayed CUDA graph does): the apply
+        # kernels consumed the flags, and the ranks are synchronised between replays
+        a.gate_dev(st.cuda_stream)
+        a.bestfit_batches_shard_dev(batches, 0, st.cuda_stream, inputs_ready=True)
+        a.apply_peers_multi_dev(0, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
+        a.gate_open()
+        torch.cuda.synchronize()
+        peer_conn.send("replayed")
+        assert peer_conn.recv() == "replayed"
+    out = [(idx.cpu().numpy(), dl.cpu().numpy(), tab.cpu().numpy()) for c, m, idx, dl, tab in tens]
+    conn.send((rank, out, a.peer_last_timeout))
+    peer_conn.send("done")
+    peer_conn.recv()
+    a.peer_detach()
+    a.close()
+
+
+def test_world2_cfg4_sharded_multi_batch_with_gate(oracle_c, egpu):
+    """BASELINE config 4's shape (64 devices, request rows sharded over the ranks) at world = 2:
+    lookup scan + fused peer push out of a multi-batch launch, start gate, batched apply."""
+    import torch.multiprocessing as mp
+    from elastic_gpu_agent_b200 import sharding
+    ctx = mp.get_context("spawn")
+    K, R, D = 12, 30_001, 64
+    a_conn, b_conn = ctx.Pipe()
+    res0_r, res0_w = ctx.Pipe(False)
+    res1_r, res1_w = ctx.Pipe(False)
+    p0 = ctx.Process(target=_multi_rank_main, args=(0, 2, res0_w, a_conn, K, R, 3))
+    p1 = ctx.Process(target=_multi_rank_main, args=(1, 2, res1_w, b_conn, K, R, 3))
+    p0.start()
+    p1.start()
+    assert res0_r.poll(180) and res1_r.poll(180), "ranks did not finish"
+    r0, r1 = res0_r.recv(), res1_r.recv()
+    p0.join(60)
+    p1.join(60)
+    assert p0.exitcode == 0 and p1.exitcode == 0
+    assert r0[2] == 0 and r1[2] == 0, "a gate or an apply kernel timed out waiting for its peer"
+    w = egpu.synth.workload("cfg4")
+    for k in range(K):
+        tot = np.zeros(2 * D, dtype=np.int64)
+        for rank, res in ((0, r0), (1, r1)):
+            rc, rm = egpu.synth.requests(4, 40 + k, R, first_row=rank * R)
+            o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm)
+            idx, dl, _ = res[1][k]
+            assert np.array_equal(idx, o_idx), f"indices rank {rank} batch {k}"
+            assert np.array_equal(dl, np.concatenate([o_dc, o_dm]))
+            tot += np.concatenate([o_dc, o_dm])
+        etab = sharding.combine_demands(w["free_core"], w["free_mem"], tot[None, :])
+        assert np.array_equal(r0[1][k][2], etab) and np.array_equal(r1[1][k][2], etab)
+
+
 # ------------------------------------------------------------------ prefix-commit over shards
 def _rank_partial(idx, rc, rm, D):
     d = np.zeros(2 * D, dtype=np.int64)

@@ -1,5 +1,5 @@
 """GetPreferredAllocation's host logic (elastic-gpu-agent_b200/csrc/egpu_plugin.cc) on CPU: the
-file is linked against recording stand-ins for egpu_table_set / egpu_bestfit_batch
+file is linked against a recording stand-in for egpu_bestfit_query
 (tests/plugin_host_harness.cc).  Checked here: the availability table built from the ID strings,
 must-include pinning, the request handed to the scan, and the IDs chosen for the scan's answer -
 the answer itself is scripted from the oracle (the CUDA scan is checked in the gpu tests)."""
