@@ -33,6 +33,8 @@ using namespace egpu;
 
 namespace {
 
+constexpr int64_t kMaxRows = (1ll << 31) - 1;  // EGPU_MAX_ROWS
+
 template <int DT, int THREADS>
 SnapLaunch make_launch(bool grid_variant) {
     SnapLaunch l;
@@ -119,6 +121,9 @@ int configure_launch(egpu_ctx* ctx, SnapLaunch& l, int D, bool grid_variant, boo
         if (ctx->lut_acc == 0) {
             l.lut_fn = contig ? bestfit_lut_kernel<256, true, 0> : bestfit_lut_kernel<256, false, 0>;
             l.smem = sizeof(LutSmem<256, 0>);
+        } else if (ctx->lut_acc == 2) {
+            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 2> : bestfit_lut_kernel<256, false, 2>;
+            l.smem = sizeof(LutSmem<256, 2>);
         } else {
             l.lut_fn = contig ? bestfit_lut_kernel<256, true, 1> : bestfit_lut_kernel<256, false, 1>;
             l.smem = sizeof(LutSmem<256, 1>);
@@ -146,6 +151,7 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
                     long long* d_delta, int32_t* d_table_out, int user_flags, bool finalize, cudaStream_t s,
                     int rpt_hint = 0, unsigned long long push_step_plus1 = 0, bool contig = false, int* n_tiles_out = nullptr,
                     int lag = 0) {
+    if (R > kMaxRows) return EGPU_ERR_INVALID;  // the scans index 128-bit vectors with 32 bits
     const bool grid_variant = ctx->variant == EGPU_VARIANT_GRID;
     const bool lut_variant = ctx->variant == EGPU_VARIANT_LUT || (ctx->variant == EGPU_VARIANT_AUTO && ctx->D > 16);
     const int bucket = ctx->D <= 8 ? 0 : ctx->D <= 16 ? 1 : ctx->D <= 32 ? 2 : 3;
@@ -285,9 +291,10 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     if (l.ctas_per_sm == 0) {
         int per_sm = 0;
         if (lut_variant) {
-            l.lut_fn = ctx->lut_acc == 0 ? bestfit_lut_multi_kernel<256, 0> : bestfit_lut_multi_kernel<256, 1>;
+            l.lut_fn = ctx->lut_acc == 0 ? bestfit_lut_multi_kernel<256, 0>
+                       : ctx->lut_acc == 2 ? bestfit_lut_multi_kernel<256, 2> : bestfit_lut_multi_kernel<256, 1>;
             l.threads = 256;
-            l.smem = ctx->lut_acc == 0 ? sizeof(LutSmem<256, 0>) : sizeof(LutSmem<256, 1>);
+            l.smem = ctx->lut_acc == 0 ? sizeof(LutSmem<256, 0>) : ctx->lut_acc == 2 ? sizeof(LutSmem<256, 2>) : sizeof(LutSmem<256, 1>);
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
@@ -351,16 +358,27 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     const int64_t nvec = max_r >> 2;
     const int64_t per_cta = static_cast<int64_t>(l.threads) * ((ctx->multi_rpt + 3) / 4);
     int64_t tiles = (nvec + per_cta - 1) / per_cta;
+    if (tiles < 1) tiles = 1;
     int per_sm = l.ctas_per_sm;
     if (ctx->ctas_per_sm_cap > 0 && ctx->ctas_per_sm_cap < per_sm) per_sm = ctx->ctas_per_sm_cap;
-    int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * ctx->multi_waves / K;
-    if (tiles > cap) tiles = cap;
-    if (tiles < 1) tiles = 1;
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * ctx->multi_waves;  // CTAs resident at once (x waves)
+    int64_t extra = 0;
+    if (tiles * K > cap) {  // capped: hand the resident CTAs out evenly, the first `extra` batches get one more
+        tiles = cap / K;
+        extra = cap % K;
+        if (tiles < 1) {
+            tiles = 1;
+            extra = 0;
+        }
+    }
+    if (tiles > 0xffff) tiles = 0xffff;
     if (max_r / (tiles * l.threads) + 8 >= (1ll << 19)) return EGPU_ERR_INVALID;  // lane-private sums hold 2^19 rows per lane
+    const int tiles_extra = static_cast<int>(tiles | (extra << 16));
+    const int64_t n_ctas = tiles * K + extra;
 
     const unsigned int slot_base = static_cast<unsigned int>(ctx->mseq % kMultiSlots);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(tiles * K));
+    cfg.gridDim = dim3(static_cast<unsigned>(n_ctas));
     cfg.blockDim = dim3(static_cast<unsigned>(l.threads));
     cfg.dynamicSmemBytes = l.smem;
     cfg.stream = s;
@@ -370,10 +388,10 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (lut_variant)
-        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.lut_fn, ctx->d_state, args, static_cast<int>(tiles), flags, slot_base, push_base,
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.lut_fn, ctx->d_state, args, tiles_extra, flags, slot_base, push_base,
                                           static_cast<const DevLut*>(ctx->d_lut)));
     else
-        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, args, static_cast<int>(tiles), flags, slot_base, push_base));
+        EGPU_CUDA(ctx, cudaLaunchKernelEx(&cfg, l.fn, ctx->d_state, args, tiles_extra, flags, slot_base, push_base));
     ctx->launches += 1;
     ctx->mseq += static_cast<uint64_t>(K);
     add_inflight(ctx, mine, n_mine);
@@ -641,7 +659,8 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
             const int v = std::atoi(e);
             ctx->threads8 = (v == 128 || v == 512) ? v : 256;
         }
-        if (const char* e = std::getenv("EGPU_LUT_ACC")) ctx->lut_acc = std::strcmp(e, "atomic3") == 0 ? 0 : 1;
+        if (const char* e = std::getenv("EGPU_LUT_ACC"))
+            ctx->lut_acc = std::strcmp(e, "atomic3") == 0 ? 0 : std::strcmp(e, "pair") == 0 ? 2 : 1;
         if (const char* e = std::getenv("EGPU_LONE_FIRST")) ctx->lone_first = std::atoi(e) != 0;
         if (const char* e = std::getenv("EGPU_MULTI_WAVES")) ctx->multi_waves = std::max(1, std::min(8, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_MULTI_RPT")) ctx->multi_rpt = std::max(4, std::min(4096, std::atoi(e)));
@@ -822,7 +841,7 @@ static int check_batches(const egpu_batch* batches, int32_t K) {
     if (!batches || K < 1 || K > EGPU_MAX_BATCHES) return EGPU_ERR_INVALID;
     for (int k = 0; k < K; ++k) {
         const egpu_batch& b = batches[k];
-        if (b.R < 0) return EGPU_ERR_INVALID;
+        if (b.R < 0 || b.R > kMaxRows) return EGPU_ERR_INVALID;
         if (b.R > 0 && (!b.d_req_core || !b.d_req_mem || !b.d_out_idx)) return EGPU_ERR_INVALID;
         if (!aligned16(b.d_req_core) || !aligned16(b.d_req_mem) || !aligned16(b.d_out_idx)) return EGPU_ERR_INVALID;
     }
@@ -874,7 +893,7 @@ int egpu_peer_gate_open(egpu_ctx* ctx) {
 
 int egpu_bestfit_query(egpu_ctx* ctx, const int32_t* free_core, const int32_t* free_mem, int32_t D, const int32_t* req_core,
                        const int32_t* req_mem, int64_t R, int32_t* out_idx) {
-    if (!ctx || !free_core || !free_mem || D < 1 || D > EGPU_MAX_DEVICES || R < 0) return EGPU_ERR_INVALID;
+    if (!ctx || !free_core || !free_mem || D < 1 || D > EGPU_MAX_DEVICES || R < 0 || R > kMaxRows) return EGPU_ERR_INVALID;
     if (R > 0 && (!req_core || !req_mem || !out_idx)) return EGPU_ERR_INVALID;
     for (int d = 0; d < D; ++d) {
         if (free_core[d] < 0 || free_core[d] > EGPU_CORE_MAX) return EGPU_ERR_INVALID;

@@ -89,7 +89,7 @@ struct egpu_ctx {
     std::vector<Range> inflight;      // output ranges of those launches, sorted by address, pairwise disjoint
     std::vector<Range> range_tmp;
     Range multi_ranges[3 * kMultiMax];  // scratch of launch_multi
-    int lone_first = 1;               // a launch that cannot overlap a predecessor gets the lone-launch grid even on a
+    int lone_first = 0;               // a launch that cannot overlap a predecessor gets the lone-launch grid even on a
                                       // stream declared pipelined (EGPU_LONE_FIRST=0: round 1's sizing, for A/B)
     int multi_waves = 1;              // multi-batch launches: CTA waves the grid may hold (EGPU_MULTI_WAVES)
     int multi_rpt = 8;                // ... and the fewest rows per thread worth a CTA (EGPU_MULTI_RPT)

@@ -130,16 +130,19 @@ static_assert(sizeof(MultiArgs) <= 3072, "descriptors + the scalar arguments mus
 // table lookup  a2[c][rank(m)]  (device id, 0xFF = none; a2[c] = the row of position start[c]).
 // rank(m) comes from a bucket table over m >> 6.  Entry = lo << 8 | t:
 //   lo = #V below the bucket (0..64);  t = (threshold & 63) + 1 when exactly one value of V
-//   lies in the bucket, 64 when none (so  (m & 63) >= t  is  "threshold < m"), and bit 15 is
-//   set when several do (rare: the scan then walks v[] from lo).
+//   lies in the bucket, 64 when none (so  (m & 63) >= t  is  "threshold < m").  When several
+//   values of V share a bucket (at most 32 buckets can be like that) bit 15 is set and bits
+//   8..14 name a 64-byte block of ovf[]: ovf[block][m & 63] is rank(m) itself.  One predicated
+//   extra read for those requests, no loop and no divergent region in the scan.
 constexpr int kLutStride = kMaxD + 1;
 constexpr int kLutBuckets = (1 << 18 >> 6) + 1;  // last bucket: mem clamped to 2^18 = out of domain
 constexpr int kLutCRows = kCoreMax + 2;          // c = 0..100, and 101 = "core out of domain" (all 0xFF)
-constexpr uint32_t kLutMulti = 0x8000u;
+constexpr uint32_t kLutMulti = 0x80u;
 struct DevLut {
     uint16_t bucket[kLutBuckets + 7];
     uint8_t a2[kLutCRows * kLutStride + 10];
-    uint32_t v[kMaxD + 4];  // ascending distinct fm values, 0xFFFFFFFF past nv (sentinel for the walk)
+    uint8_t ovf[(kMaxD / 2) * 64];
+    uint32_t v[kMaxD + 4];  // ascending distinct fm values, 0xFFFFFFFF past nv (kept for inspection; the scan does not read it)
     int32_t nv;
     int32_t pad_[3];
 };
@@ -166,6 +169,9 @@ __device__ __forceinline__ int4 ld_stream_v4(const int32_t* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ int4 ld_stream_v4(const int4* p) { return ld_stream_v4(reinterpret_cast<const int32_t*>(p)); }
+__device__ __forceinline__ void st_stream_v4(int32_t* p, const int4& v);
+__device__ __forceinline__ void st_stream_v4(int4* p, const int4& v) { st_stream_v4(reinterpret_cast<int32_t*>(p), v); }
 __device__ __forceinline__ void st_stream_v4(int32_t* p, const int4& v) {
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                  "r"(v.y), "r"(v.z), "r"(v.w)
@@ -177,6 +183,8 @@ __device__ __forceinline__ void st_stream_v4(int32_t* p, const int4& v) {
 // previous launch has completed and its writes are visible.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ int32_t sat_i32(long long v) {
     return v > 2147483647LL ? 2147483647 : (v < -2147483648LL ? static_cast<int32_t>(-2147483648LL) : static_cast<int32_t>(v));

@@ -24,6 +24,7 @@ namespace egpu {
 // 3-input unsigned min (VIMNMX3).  The chosen position maps back to the device
 // index through a shared-memory tile.
 
+constexpr int kDevTile = kMaxD + 8;  // positions 0..63, and "none" = 32 (DT <= 32) or 64
 template <int DT, int THREADS>
 struct SnapSmem {
     int32_t sFc[kMaxD];                           // table tile (grid variant; re-sort scratch)
@@ -31,7 +32,7 @@ struct SnapSmem {
     int32_t sPosDev[kMaxD];
     unsigned long long sWarpAcc[THREADS / 32][2 * DT];
     int sLast;
-    int32_t sDevTile[THREADS / 32][DT + 8];           // warp-private: sorted position -> device, [DT] = -1
+    int32_t sDevTile[THREADS / 32][kDevTile];         // warp-private: sorted position -> device, -1 from DT on
     unsigned long long hist[THREADS / 32][DT + 1][32];  // lane-private demand sums; row 0 = "no device"
 };
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void resort_table_cta(DevState* st, int D, int32_t* s
     }
 }
 
-// First feasible sorted position; >= DT when there is none.
+// First feasible sorted position; kNoCand (DT <= 32) or DT (DT = 64) when there is none.
 // Per (request, row) pair: one subtract (IMAD.IADD or IADD3, ptxas balances the FMA and
 // ALU pipes), one 3-input LOP3 ((t ^ G) & M, both masks in registers), half a VIMNMX3.
 template <int N>
@@ -87,7 +88,7 @@ __device__ __forceinline__ uint32_t first_feasible32(const uint32_t* K, uint32_t
 template <int DT>
 __device__ __forceinline__ uint32_t first_feasible(const uint32_t (&K)[DT], uint32_t q, uint32_t gx, uint32_t gm) {
     if constexpr (DT <= 32) {
-        return min(first_feasible32<DT>(K, q, gx, gm), static_cast<uint32_t>(DT));
+        return first_feasible32<DT>(K, q, gx, gm);  // 0..DT-1, or kNoCand (= 32): the tile maps both ranges
     } else {  // positions are stored mod 32: two halves
         const uint32_t lo = first_feasible32<32>(K, q, gx, gm);
         const uint32_t hi = first_feasible32<DT - 32>(K + 32, q, gx, gm);
@@ -158,7 +159,9 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         if (tot) atomicAdd(&ep.acc[tid < D ? tid : kMaxD + (tid - D)], tot);
         // prefix-commit mode: this CTA owns a contiguous run of rows; keep its sums per device
         if (tile_sums) tile_sums[static_cast<size_t>(ec.tile) * 2 * kMaxD + (tid < D ? tid : kMaxD + (tid - D))] = tot;
-        __threadfence();  // only the threads that published sums need to order them before the ticket
+        // release: only the threads that published sums need to order them before the ticket
+        // (acq_rel is enough for this message-passing pattern and lighter than __threadfence's fence.sc)
+        fence_acq_rel_gpu();
     }
     __syncthreads();
     if (tid == 0) {
@@ -167,7 +170,7 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
     }
     __syncthreads();
     if (!*sLast) return;
-    __threadfence();
+    fence_acq_rel_gpu();  // acquire: the other CTAs' sums, published before their tickets
     const bool fin = (flags & kFlagFinalize) != 0;
     const bool commit = fin && (flags & kFlagCommit);
     if (fin && tid < D) {
@@ -307,15 +310,19 @@ __device__ __forceinline__ int sorted_scan_rows(SnapSmem<DT, THREADS>& s, DevSta
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    long long nvec = R >> 2;  // CONTIG: end of this CTA's tile
-    long long stride = static_cast<long long>(n_tiles) * THREADS;
-    long long v = static_cast<long long>(tile_i) * THREADS + tid;
+    // 32-bit vector indices (the entry points keep R below 2^31): one IMAD.WIDE per address, 32-bit compares
+    const int4* __restrict__ vc = reinterpret_cast<const int4*>(req_core);
+    const int4* __restrict__ vm = reinterpret_cast<const int4*>(req_mem);
+    int4* __restrict__ vo = reinterpret_cast<int4*>(out_idx);
+    int nvec = static_cast<int>(R >> 2);  // CONTIG: end of this CTA's tile
+    int stride = n_tiles * THREADS;
+    int v = tile_i * THREADS + tid;
     if (CONTIG) {
-        const long long per = (nvec + n_tiles - 1) / n_tiles;
-        const long long lo = static_cast<long long>(tile_i) * per;
-        nvec = (lo + per < nvec) ? lo + per : nvec;
+        const int per = (nvec + n_tiles - 1) / n_tiles;
+        const long long lo = static_cast<long long>(tile_i) * per;  // may exceed nvec on a capped grid
+        nvec = (lo + per < nvec) ? static_cast<int>(lo + per) : nvec;
         stride = THREADS;
-        v = lo + tid;
+        v = lo < nvec ? static_cast<int>(lo) + tid : nvec;
     }
 
     // issue the first tile's loads before anything else: the request stream is
@@ -323,12 +330,12 @@ __device__ __forceinline__ int sorted_scan_rows(SnapSmem<DT, THREADS>& s, DevSta
     int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
     bool has0 = v < nvec, has1 = (v + stride) < nvec;
     if (has0) {
-        c0 = ld_stream_v4(req_core + 4 * v);
-        m0 = ld_stream_v4(req_mem + 4 * v);
+        c0 = ld_stream_v4(vc + v);
+        m0 = ld_stream_v4(vm + v);
     }
     if (has1) {
-        c1 = ld_stream_v4(req_core + 4 * (v + stride));
-        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
+        c1 = ld_stream_v4(vc + (v + stride));
+        m1 = ld_stream_v4(vm + (v + stride));
     }
 
     // sorted table rows: uniform loads straight into registers, no barrier
@@ -340,15 +347,16 @@ __device__ __forceinline__ int sorted_scan_rows(SnapSmem<DT, THREADS>& s, DevSta
         K[j] = k4.x; K[j + 1] = k4.y; K[j + 2] = k4.z; K[j + 3] = k4.w;
     }
     const uint32_t gx = st->cand_xor, gm = st->cand_mask;
-    // warp-private tile of the position -> device map: only a warp-level barrier
+    // warp-private tile of the position -> device map: only a warp-level barrier.  "No feasible
+    // row" comes out of first_feasible as DT (D > 32) or as kNoCand = 32 (DT <= 32): both map to -1.
     int32_t* tile = s.sDevTile[warp];
-    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
+    for (int j = lane; j < kDevTile; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
     hist_zero<DT, THREADS>(s, warp, lane);
     __syncwarp();
 
     auto decide = [&](int32_t core, int32_t mem) -> int32_t {
         const uint32_t best = first_feasible<DT>(K, pack_request_word(core, mem), gx, gm);
-        const int32_t idx = tile[best];  // best <= DT; tile[DT] = -1
+        const int32_t idx = tile[best];
         hist_add<DT, THREADS>(s, warp, lane, idx, core, mem);
         return idx;
     };
@@ -362,19 +370,19 @@ __device__ __forceinline__ int sorted_scan_rows(SnapSmem<DT, THREADS>& s, DevSta
     };
 
     while (has0) {
-        const long long vn = v + 2 * stride;
+        const int vn = v + 2 * stride;
         const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
         int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
         if (nhas0) {
-            nc0 = ld_stream_v4(req_core + 4 * vn);
-            nm0 = ld_stream_v4(req_mem + 4 * vn);
+            nc0 = ld_stream_v4(vc + vn);
+            nm0 = ld_stream_v4(vm + vn);
         }
         if (nhas1) {
-            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
-            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
+            nc1 = ld_stream_v4(vc + (vn + stride));
+            nm1 = ld_stream_v4(vm + (vn + stride));
         }
-        st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
+        st_stream_v4(vo + v, decide4(c0, m0));
+        if (has1) st_stream_v4(vo + (v + stride), decide4(c1, m1));
         v = vn;
         has0 = nhas0;
         has1 = nhas1;
@@ -411,6 +419,25 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
     if (late && !boundary) pdl_wait();  // do not complete before the predecessor has: keeps stream order transitive
 }
 
+// Grid of a multi-batch launch: the first `extra` batches have base + 1 tiles (CTAs), the others
+// base, so that K * base + extra can be exactly the number of CTAs the GPU holds at once (every SM
+// equally loaded) whatever K is.  tiles_extra = base | extra << 16.
+__device__ __forceinline__ void multi_cta_to_tile(int tiles_extra, int& batch, int& tile_i, int& tiles) {
+    const int base = tiles_extra & 0xffff, extra = tiles_extra >> 16;
+    const int bid = static_cast<int>(blockIdx.x);
+    const int cut = extra * (base + 1);
+    if (bid < cut) {
+        tiles = base + 1;
+        batch = bid / tiles;
+        tile_i = bid - batch * tiles;
+    } else {
+        tiles = base;
+        const int b2 = (bid - cut) / base;
+        batch = extra + b2;
+        tile_i = (bid - cut) - b2 * base;
+    }
+}
+
 // Multi-batch launch (egpu_bestfit_batches_dev): K independent batches, all scored against the
 // same table, in ONE grid.  CTA (b, t) = tile t of batch b; every batch has its own epilogue
 // slot, so its last CTA publishes that batch's demand sums / table' (and pushes its exchange
@@ -419,7 +446,7 @@ bestfit_sorted_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req
 // eating at R = 1 M, and the launch floor at R = 1 k .. 100 k.
 template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-bestfit_sorted_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles, int flags,
+bestfit_sorted_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles_extra, int flags,
                             unsigned int slot_base, unsigned long long push_base) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& s = *reinterpret_cast<SnapSmem<DT, THREADS>*>(smem_raw);
@@ -427,9 +454,9 @@ bestfit_sorted_multi_kernel(DevState* __restrict__ st, const __grid_constant__ M
     const bool boundary = (flags & kFlagBoundary) != 0;
     if (!late) pdl_wait();
     if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
-    const int batch = static_cast<int>(blockIdx.x) / tiles;
-    const int tile_i = static_cast<int>(blockIdx.x) - batch * tiles;
-    const BatchDesc& b = args.b[batch];
+    int batch, tile_i, tiles;
+    multi_cta_to_tile(tiles_extra, batch, tile_i, tiles);
+    const BatchDesc b = args.b[batch];  // one read of the parameter space, then registers
     const int D = sorted_scan_rows<DT, THREADS, false>(s, st, b.rc, b.rm, b.R, b.idx, tile_i, tiles);
     if (boundary) {
         pdl_wait();
@@ -488,7 +515,7 @@ bestfit_sorted_packed_kernel(DevState* __restrict__ st, const uint32_t* __restri
     }
     const uint32_t gx = st->cand_xor, gm = st->cand_mask;
     int32_t* tile = s.sDevTile[warp];
-    for (int j = lane; j <= DT; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
+    for (int j = lane; j < kDevTile; j += 32) tile[j] = j < DT ? st->sorted_dev[j] : -1;
     hist_zero<DT, THREADS>(s, warp, lane);
     __syncwarp();
 
@@ -597,7 +624,7 @@ bestfit_grid_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_c
 __global__ void __launch_bounds__(256)
 lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
     __shared__ uint32_t sFm[kMaxD], sFcs[kMaxD], sV[kMaxD + 4];
-    __shared__ int sFirst[kMaxD], sRidx[kMaxD], sNv;
+    __shared__ int sFirst[kMaxD], sRidx[kMaxD], sNv, sBlocks;
     __shared__ uint8_t sA[kLutStride * kLutStride];  // a[srow][rank]: first device at or after srow with ridx >= rank
     __shared__ uint8_t sStart[kLutCRows];
     const int tid = threadIdx.x;
@@ -625,6 +652,7 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
         int nv = 0;
         for (int k = 0; k < D; ++k) nv += sFirst[k];
         sNv = nv;
+        sBlocks = 0;
         lut->nv = nv;
     }
     __syncthreads();
@@ -657,10 +685,20 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
             hi += (sV[k] < hi_v);
         }
         const int n = hi - lo;
-        uint32_t e = static_cast<uint32_t>(lo) << 8;
-        if (n == 0) e |= 64u;
-        else if (n == 1) e |= (sV[lo] & 63u) + 1u;
-        else e |= kLutMulti | 64u;
+        uint32_t e = static_cast<uint32_t>(lo);
+        if (n == 0) {
+            e |= 64u << 8;
+        } else if (n == 1) {
+            e |= ((sV[lo] & 63u) + 1u) << 8;
+        } else {  // several thresholds in this bucket: exact ranks for its 64 values of m
+            const int blk = atomicAdd(&sBlocks, 1);  // < 32: two values per block at least, 64 values in all
+            e = kLutMulti | static_cast<uint32_t>(blk) | (64u << 8);
+            for (uint32_t x = 0; x < 64u; ++x) {
+                int r = lo;
+                for (int k = lo; k < hi; ++k) r += (sV[k] < lo_v + x);
+                lut->ovf[blk * 64 + x] = static_cast<uint8_t>(r);
+            }
+        }
         lut->bucket[b] = static_cast<uint16_t>(e);
     }
 }
@@ -678,6 +716,13 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
 //            spread over the banks), infeasible rows into a per-lane dummy word: no branches,
 //            no shared hot spot.  A copy receives 4 lanes x 8 rows per trip, so word 0's 12-bit
 //            mem >> 16 field (<= 3 per add) lasts 42 trips: fold every 32.
+//   ACC = 2  no atomics: 64-bit sums (core << 38 | mem, as the register scan keeps them) in columns
+//            owned by lane pairs; the two half-warps take turns (two phases per trip, __syncwarp
+//            between them).  A half-warp read or write of a column set is ONE conflict-free
+//            wavefront, so a decision costs 4 shared-memory wavefronts per warp instead of the
+//            ~7.7 the two adds of ACC 1 take with their bank conflicts - the lookup scan is bound by
+//            the shared-memory pipe (ncu: l1tex data pipe 79 % busy), not by issue slots.  8.3 KB
+//            per warp; no folding needed below 2^19 rows per lane.
 constexpr int kLutFlushTrips3 = 128;  // ACC 0: x 8 rows per thread per trip x 32 lanes = 32 K rows per warp
 constexpr int kLutFlushTrips2 = 32;   // ACC 1
 constexpr int kLutCopies = 8;
@@ -689,7 +734,9 @@ struct LutSmem {
     unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
     int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     int sLast;
-    alignas(16) uint32_t hist32[THREADS / 32][ACC == 0 ? 3 * kMaxD : kLutCopies * kLutCopyStride];
+    // ACC 0 / 1: 32-bit words for ATOMS.ADD; ACC 2: 64-bit sums, one column per lane PAIR (lane, lane ^ 16),
+    // [device + 1][lane & 15] - bank = 2 * (lane & 15): conflict-free, a half-warp access is one wavefront
+    alignas(16) uint32_t hist32[THREADS / 32][ACC == 0 ? 3 * kMaxD : ACC == 1 ? kLutCopies * kLutCopyStride : (kMaxD + 1) * 16 * 2];
 };
 
 // The lookup scan of one batch by one CTA (tile `tile_i` of `n_tiles`, as sorted_scan_rows).
@@ -702,25 +749,29 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    long long nvec = R >> 2;
-    long long stride = static_cast<long long>(n_tiles) * THREADS;
-    long long v = static_cast<long long>(tile_i) * THREADS + tid;
+    const int4* __restrict__ vc = reinterpret_cast<const int4*>(req_core);
+    const int4* __restrict__ vm = reinterpret_cast<const int4*>(req_mem);
+    int4* __restrict__ vo = reinterpret_cast<int4*>(out_idx);
+    int nvec = static_cast<int>(R >> 2);
+    int stride = n_tiles * THREADS;
+    int v = tile_i * THREADS + tid;
     if (CONTIG) {
-        const long long per = (nvec + n_tiles - 1) / n_tiles;
+        const int per = (nvec + n_tiles - 1) / n_tiles;
         const long long lo = static_cast<long long>(tile_i) * per;
-        nvec = (lo + per < nvec) ? lo + per : nvec;
+        nvec = (lo + per < nvec) ? static_cast<int>(lo + per) : nvec;
         stride = THREADS;
-        v = lo + tid;
+        v = lo < nvec ? static_cast<int>(lo) + tid : nvec;
     }
-    int4 c0 = make_int4(0, 0, 0, 0), m0 = c0, c1 = c0, m1 = c0;
+    // vectors past the end stay (-1, -1): infeasible requests, which land in the lane's dummy word
+    int4 c0 = make_int4(-1, -1, -1, -1), m0 = c0, c1 = c0, m1 = c0;
     bool has0 = v < nvec, has1 = (v + stride) < nvec;
     if (has0) {
-        c0 = ld_stream_v4(req_core + 4 * v);
-        m0 = ld_stream_v4(req_mem + 4 * v);
+        c0 = ld_stream_v4(vc + v);
+        m0 = ld_stream_v4(vm + v);
     }
     if (has1) {
-        c1 = ld_stream_v4(req_core + 4 * (v + stride));
-        m1 = ld_stream_v4(req_mem + 4 * (v + stride));
+        c1 = ld_stream_v4(vc + (v + stride));
+        m1 = ld_stream_v4(vm + (v + stride));
     }
     // shared-memory tile of the lookup tables (15 KB, L2-resident source)
     {
@@ -742,21 +793,20 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
     uint32_t* const hcopy = hw + (ACC == 1 ? (lane >> 2) * kLutCopyStride : 0);
     const uint32_t dummy_col = static_cast<uint32_t>(kMaxD) + (static_cast<uint32_t>(lane) & 3u);
 
-    // device (0..63) or 0xFF for one request: two dependent shared-memory reads on the common path
+    // device (0..63) or 0xFF for one request: two dependent shared-memory reads, no branch
+    // (the read of ovf[] is predicated: only requests whose bucket holds several thresholds)
     auto lookup = [&](int32_t core, int32_t mem) -> uint32_t {
         const uint32_t c = min(static_cast<uint32_t>(core), static_cast<uint32_t>(kCoreMax + 1));
         const uint32_t m = min(static_cast<uint32_t>(mem), 1u << 18);
         const uint32_t e = L.bucket[m >> 6];
-        uint32_t rank = (e >> 8) & 0x7Fu;
-        if (e & kLutMulti) {  // rare: several distinct fm values inside one 64 MiB bucket
-            while (L.v[rank] < m) ++rank;
-        } else {
-            rank += ((m & 63u) >= (e & 0x7Fu)) ? 1u : 0u;
-        }
+        const uint32_t lo7 = e & 0x7Fu, x = m & 63u;
+        uint32_t rank = lo7 + (((e >> 8) - 1u - x) >> 31);  // + 1 iff x >= t
+        if (e & kLutMulti) rank = L.ovf[lo7 * 64u + x];
         return L.a2[c * kLutStride + rank];
     };
     // fold this warp's 32-bit words into the 64-bit sums and clear them
     auto flush32 = [&]() {
+        if constexpr (ACC == 2) return;
         __syncwarp();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -806,13 +856,38 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
         add1(dev, core, mem);
         return static_cast<int32_t>(static_cast<int8_t>(dev));
     };
-    auto decide4 = [&](const int4& c, const int4& m) -> int4 {
-        int4 r;
-        r.x = decide(c.x, m.x);
-        r.y = decide(c.y, m.y);
-        r.z = decide(c.z, m.z);
-        r.w = decide(c.w, m.w);
-        return r;
+    // All the lookups of a trip first, then all the adds: the shared-memory adds order every
+    // later shared-memory read behind them (the compiler cannot tell the tables apart), so
+    // interleaving them request by request makes one serial chain of eight dependent reads.
+    auto lookup4 = [&](const int4& c, const int4& m) -> uint4 {
+        return make_uint4(lookup(c.x, m.x), lookup(c.y, m.y), lookup(c.z, m.z), lookup(c.w, m.w));
+    };
+    auto add4 = [&](const uint4& d, const int4& c, const int4& m) {
+        add1(d.x, c.x, m.x);
+        add1(d.y, c.y, m.y);
+        add1(d.z, c.z, m.z);
+        add1(d.w, c.w, m.w);
+    };
+    // ACC 2: the eight requests of a trip, one half-warp at a time
+    unsigned long long* const h64 = reinterpret_cast<unsigned long long*>(hw) + (lane & 15);
+    auto add8_pair = [&](const uint4& d0, const int4& c0, const int4& m0, const uint4& d1, const int4& c1, const int4& m1) {
+        auto one = [&](uint32_t dev, int32_t core, int32_t mem) {
+            // row 0 absorbs infeasible rows (0xFF -> 0); its content is never read
+            const uint32_t row = (dev + 1u) & 0x7Fu;
+            h64[row * 16u] += (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
+                              static_cast<unsigned long long>(static_cast<uint32_t>(mem));
+        };
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            if ((lane >> 4) == p) {
+                one(d0.x, c0.x, m0.x); one(d0.y, c0.y, m0.y); one(d0.z, c0.z, m0.z); one(d0.w, c0.w, m0.w);
+                one(d1.x, c1.x, m1.x); one(d1.y, c1.y, m1.y); one(d1.z, c1.z, m1.z); one(d1.w, c1.w, m1.w);
+            }
+            __syncwarp();
+        }
+    };
+    auto as_idx4 = [](const uint4& d) -> int4 {
+        return make_int4(static_cast<int8_t>(d.x), static_cast<int8_t>(d.y), static_cast<int8_t>(d.z), static_cast<int8_t>(d.w));
     };
     constexpr int kFlushTrips = ACC == 0 ? kLutFlushTrips3 : kLutFlushTrips2;
     int trips = 0;
@@ -821,29 +896,66 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
             flush32();
             trips = 0;
         }
-        const long long vn = v + 2 * stride;
+        const int vn = v + 2 * stride;
         const bool nhas0 = vn < nvec, nhas1 = (vn + stride) < nvec;
-        int4 nc0 = make_int4(0, 0, 0, 0), nm0 = nc0, nc1 = nc0, nm1 = nc0;
+        int4 nc0 = make_int4(-1, -1, -1, -1), nm0 = nc0, nc1 = nc0, nm1 = nc0;
         if (nhas0) {
-            nc0 = ld_stream_v4(req_core + 4 * vn);
-            nm0 = ld_stream_v4(req_mem + 4 * vn);
+            nc0 = ld_stream_v4(vc + vn);
+            nm0 = ld_stream_v4(vm + vn);
         }
         if (nhas1) {
-            nc1 = ld_stream_v4(req_core + 4 * (vn + stride));
-            nm1 = ld_stream_v4(req_mem + 4 * (vn + stride));
+            nc1 = ld_stream_v4(vc + (vn + stride));
+            nm1 = ld_stream_v4(vm + (vn + stride));
         }
-        if (has0) st_stream_v4(out_idx + 4 * v, decide4(c0, m0));
-        if (has1) st_stream_v4(out_idx + 4 * (v + stride), decide4(c1, m1));
+        // no branch around the lookups (lanes past the end carry infeasible requests): the eight
+        // requests of a trip overlap their dependent reads
+        const uint4 d0 = lookup4(c0, m0);
+        const uint4 d1 = lookup4(c1, m1);
+        if (has0) st_stream_v4(vo + v, as_idx4(d0));
+        if (has1) st_stream_v4(vo + (v + stride), as_idx4(d1));
+        if constexpr (ACC == 2) {
+            add8_pair(d0, c0, m0, d1, c1, m1);
+        } else {
+            add4(d0, c0, m0);
+            add4(d1, c1, m1);
+        }
         v = vn;
         has0 = nhas0;
         has1 = nhas1;
         c0 = nc0; m0 = nm0; c1 = nc1; m1 = nm1;
     }
-    if (tile_i == (CONTIG ? n_tiles - 1 : 0) && tid < static_cast<int>(R & 3)) {  // ragged tail: R % 4 rows (the last ones)
-        const long long r = ((R >> 2) << 2) + tid;
-        out_idx[r] = decide(req_core[r], req_mem[r]);
+    if (tile_i == (CONTIG ? n_tiles - 1 : 0) && warp == 0) {  // ragged tail: R % 4 rows (the last ones), lanes 0..2 of warp 0
+        const bool mine = lane < static_cast<int>(R & 3);
+        const long long r = ((R >> 2) << 2) + lane;
+        const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
+        const uint32_t dev = lookup(c, m);
+        if (mine) out_idx[r] = static_cast<int32_t>(static_cast<int8_t>(dev));
+        if constexpr (ACC == 2) {
+            const uint4 none = make_uint4(0xFFu, 0xFFu, 0xFFu, 0xFFu);
+            const int4 z = make_int4(0, 0, 0, 0);
+            add8_pair(make_uint4(dev, 0xFFu, 0xFFu, 0xFFu), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0), none, z, z);
+        } else {
+            add1(dev, c, m);
+        }
     }
     flush32();
+    if constexpr (ACC == 2) {  // lane L adds up the 16 columns of devices L and L + 32 (rotated start: conflict-free)
+        __syncwarp();
+        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hw);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int d = lane + 32 * half;
+            unsigned long long sc = 0, smm = 0;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const unsigned long long hv = h[(d + 1) * 16 + ((k + lane) & 15)];
+                sc += hv >> kAccShift;
+                smm += hv & ((1ull << kAccShift) - 1ull);
+            }
+            acc_c[half] = sc;
+            acc_m[half] = smm;
+        }
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         sm.sWarpAcc[warp][lane + 32 * half] = acc_c[half];
@@ -879,7 +991,7 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
 // Multi-batch form of the lookup scan (see bestfit_sorted_multi_kernel).
 template <int THREADS, int ACC>
 __global__ void __launch_bounds__(THREADS)
-bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles, int flags,
+bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles_extra, int flags,
                          unsigned int slot_base, unsigned long long push_base, const DevLut* __restrict__ glut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     auto& sm = *reinterpret_cast<LutSmem<THREADS, ACC>*>(smem_raw);
@@ -887,9 +999,9 @@ bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ Mult
     const bool boundary = (flags & kFlagBoundary) != 0;
     if (!late) pdl_wait();
     if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
-    const int batch = static_cast<int>(blockIdx.x) / tiles;
-    const int tile_i = static_cast<int>(blockIdx.x) - batch * tiles;
-    const BatchDesc& b = args.b[batch];
+    int batch, tile_i, tiles;
+    multi_cta_to_tile(tiles_extra, batch, tile_i, tiles);
+    const BatchDesc b = args.b[batch];
     const int D = lut_scan_rows<THREADS, false, ACC>(sm, st, b.rc, b.rm, b.R, b.idx, glut, tile_i, tiles);
     if (boundary) {
         pdl_wait();

@@ -65,6 +65,7 @@ extern "C" {
 #define EGPU_MAX_DEVICES   64
 #define EGPU_CORE_MAX      100              /* pkg/common/const.go:4 */
 #define EGPU_MEM_MAX       ((1 << 18) - 1)  /* MiB; B200 reports 183359 */
+#define EGPU_MAX_ROWS      2147483647       /* requests per batch (R): the scans index with 32 bits */
 #define EGPU_IDX_INFEASIBLE (-1)
 #define EGPU_IDX_DEFERRED   (-2)            /* prefix-commit mode only */
 

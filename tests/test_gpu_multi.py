@@ -128,7 +128,7 @@ def test_lookup_scan_with_clustered_memory_values(alloc, oracle_c, egpu):
         assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
 
 
-@pytest.mark.parametrize("acc", ["atomic2", "atomic3"])
+@pytest.mark.parametrize("acc", ["atomic2", "atomic3", "pair"])
 def test_lookup_scan_sums_survive_many_trips(acc, oracle_c, egpu, monkeypatch):
     """Every request lands on one device with the largest addends: the 32-bit shared-memory words
     of the lookup scan must be folded before any field overflows (4 M rows on 4 CTAs: 4096 rows
