@@ -258,9 +258,9 @@ class Leg:
                               torch.zeros(3 * D, dtype=torch.int32, device=dev)))
         self._arrs = {}
 
-    def tup(self, k, sharded):
+    def tup(self, k, with_table=True):
         c, m, i, dl, to = self.ring[k % self.nb]
-        return (c.data_ptr(), m.data_ptr(), self.R, i.data_ptr(), dl.data_ptr(), 0 if sharded else to.data_ptr())
+        return (c.data_ptr(), m.data_ptr(), self.R, i.data_ptr(), dl.data_ptr(), to.data_ptr() if with_table else 0)
 
     def chunks(self, K):
         """[(k0, k1)]: multi-batch launches of the K-step region; a launch never holds the same ring
@@ -268,34 +268,36 @@ class Leg:
         per = min(MAX_BATCHES, self.nb)
         return [(k0, min(K, k0 + per)) for k0 in range(0, K, per)]
 
-    def arr(self, k0, k1, sharded):
-        key = (k0 % self.nb, k1 - k0, sharded)
+    def arr(self, k0, k1):
+        key = (k0 % self.nb, k1 - k0)
         if key not in self._arrs:
-            self._arrs[key] = self.alloc.make_batches([self.tup(k, sharded) for k in range(k0, k1)])
+            self._arrs[key] = self.alloc.make_batches([self.tup(k) for k in range(k0, k1)])
         return self._arrs[key]
 
-    def issue(self, K, scan_stream, apply_stream=None, record=None, wait=None):
-        """K steps.  Single GPU: multi-batch launches.  Sharded (apply_stream given): every launch also
-        pushes its batches' demand vectors to the peers (exchange steps 0..K-1) and one apply launch
-        per chunk on the second stream waits for them - ordered by DATA, not by stream; the scans of
-        chunk j wait for the applies of chunk j - 2 (<= 128 steps ahead: inside the 256 slots)."""
-        sharded = apply_stream is not None
+    def issue(self, K, scan_stream, mode="single", apply_stream=None, record=None, wait=None):
+        """K steps as multi-batch launches.  mode "single": one GPU.  "fused": every launch also pushes its
+        batches' demand vectors to the peers (exchange steps 0..K-1) and the last CTA of every batch waits
+        for the peers' vectors of its step and writes table' - one launch per chunk, one stream.  "apply":
+        the push is fused, table' comes from one apply launch per chunk on a second stream (ordered by
+        DATA, not by stream; the scans of chunk j wait for the applies of chunk j - 2)."""
         done = {}
         for j, (k0, k1) in enumerate(self.chunks(K)):
-            if sharded:
+            if mode == "single":
+                self.alloc.bestfit_batches_dev(self.arr(k0, k1), scan_stream.cuda_stream, inputs_ready=True)
+            elif mode == "fused":
+                self.alloc.bestfit_batches_shard_dev(self.arr(k0, k1), k0, scan_stream.cuda_stream, inputs_ready=True, apply=True)
+            else:
                 if j >= 2:
                     wait(scan_stream, done[j - 2])
-                self.alloc.bestfit_batches_shard_dev(self.arr(k0, k1, True), k0, scan_stream.cuda_stream, inputs_ready=True)
+                self.alloc.bestfit_batches_shard_dev(self.arr(k0, k1), k0, scan_stream.cuda_stream, inputs_ready=True)
                 self.alloc.apply_peers_multi_dev(k0, [self.ring[k % self.nb][4].data_ptr() for k in range(k0, k1)], False,
                                                  apply_stream.cuda_stream)
                 done[j] = record(apply_stream)
-            else:
-                self.alloc.bestfit_batches_dev(self.arr(k0, k1, False), scan_stream.cuda_stream, inputs_ready=True)
-        return len(self.chunks(K)) * (2 if sharded else 1)
+        return len(self.chunks(K)) * (2 if mode == "apply" else 1)
 
     def issue_single_calls(self, K, stream):
         for k in range(K):
-            t = self.tup(k, False)
+            t = self.tup(k)
             self.alloc.bestfit_dev(t[0], t[1], self.R, t[3], t[4], t[5], False, stream.cuda_stream, inputs_ready=True)
 
 
@@ -354,8 +356,9 @@ def main():
     ap.add_argument("--workload", default="cfg3_1m", help="cfg2 | cfg3 | cfg3_1m | cfg4 | cfg3_64mi")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: demand vectors pushed to peer memory by the scan kernel (default) or NCCL all-gather + apply_deltas")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-apply", "nccl"],
+                    help="N > 1: demand vectors pushed to peer memory by the scan kernel, table' written by the same launch "
+                         "(peer, default) or by apply launches on a second stream (peer-apply); or NCCL all-gather + apply_deltas")
     ap.add_argument("--force-peer", action="store_true", help="experiment: the sharded step structure even at N = 1 (exchange with self)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
     args = ap.parse_args()
@@ -401,9 +404,11 @@ def main():
     D, R, nb = leg.D, leg.R, leg.nb
     torch.cuda.synchronize()
 
-    use_peer = (world > 1 and args.exchange == "peer") or args.force_peer
+    use_peer = (world > 1 and args.exchange in ("peer", "peer-apply")) or args.force_peer
     use_nccl = world > 1 and args.exchange == "nccl"
-    apply_stream = torch.cuda.Stream() if use_peer else None
+    two_stream = use_peer and args.exchange == "peer-apply"
+    apply_stream = torch.cuda.Stream() if two_stream else None
+    mode = "apply" if two_stream else "fused" if use_peer else "single"
     if use_peer:
         handles = [None] * world
         if world > 1:
@@ -436,7 +441,7 @@ def main():
                 c, m, idx, dl, to = lg.ring[k % lg.nb]
                 sharding.sharded_step(alloc, c.data_ptr(), m.data_ptr(), lg.R, idx.data_ptr(), dl, gathered, to, world, s.cuda_stream)
             return 2 * n
-        return lg.issue(n, s, aps, rec, lambda st, ev: st.wait_event(ev))
+        return lg.issue(n, s, mode, aps, rec, lambda st, ev: st.wait_event(ev))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -445,7 +450,7 @@ def main():
     def measure(lg):
         """warm-up, capture, REPLAYS timed replays of the K-step region -> (ms list, launches per region)"""
         region(lg, args.warmup, stream, apply_stream)
-        if use_peer:
+        if two_stream:
             stream.wait_stream(apply_stream)
         barrier()
         if use_nccl:  # NCCL inside a captured graph is possible but not what this variant is for: eager, one sample per replay
@@ -788,8 +793,9 @@ def main():
                        "launch": ("eager: scan launch + NCCL all-gather + apply_deltas launch per step" if use_nccl else
                                   f"the {K} steps = {n_scan} multi-batch scan launch(es) of up to {MAX_BATCHES} batches (egpu_bestfit_batches"
                                   f"{'_shard' if use_peer else ''}_dev) in one CUDA graph" +
-                                  ("; the last CTA of every batch pushes its demand vector to every peer's memory, one apply launch per "
-                                   "scan launch on a second stream (no NCCL on the data path)" if use_peer else "")),
+                                  ("; the last CTA of every batch pushes its demand vector to every peer's memory, " +
+                                   ("one apply launch per scan launch on a second stream" if two_stream else
+                                    "waits for the peers' vectors of its step and writes table'") + " (no NCCL on the data path)" if use_peer else "")),
                        "timing": f"median of {timing['replays']} replays, each behind a device-side start gate",
                        "parallelism": f"request rows sharded over {world} GPU(s), table replicated"},
             "e2e": e2e,

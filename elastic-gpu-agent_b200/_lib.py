@@ -34,6 +34,7 @@ VARIANT_LUT = 3
 F_COMMIT = 1
 F_INPUTS_READY = 2
 F_PREFIX_COMMIT = 4
+F_APPLY = 8
 IDX_DEFERRED = -2
 
 EV_ALLOC = 0

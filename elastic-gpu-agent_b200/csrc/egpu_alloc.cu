@@ -328,7 +328,8 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
         args.b[k].rm = b.d_req_mem;
         args.b[k].idx = b.d_out_idx;
         args.b[k].delta = reinterpret_cast<long long*>(b.d_delta);
-        args.b[k].table_out = push_base ? nullptr : b.d_table_out;  // sharded: table' comes from the apply
+        // sharded: table' comes from an apply call, or (EGPU_F_APPLY) from the batch's own last CTA
+        args.b[k].table_out = (push_base && !(user_flags & EGPU_F_APPLY)) ? nullptr : b.d_table_out;
         args.b[k].R = b.R;
         if (b.R > max_r) max_r = b.R;
         const uintptr_t pi = reinterpret_cast<uintptr_t>(b.d_out_idx), pd = reinterpret_cast<uintptr_t>(b.d_delta),
@@ -339,7 +340,7 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     }
     const int n_mine = prepare_ranges(mine, 3 * K);
     if (n_mine < 0) return EGPU_ERR_INVALID;  // two batches of one launch share an output: their order would be undefined
-    int flags = kFlagFinalize;
+    int flags = kFlagFinalize | ((push_base && (user_flags & EGPU_F_APPLY)) ? kFlagApplyNow : 0);
     bool pipelined = (user_flags & EGPU_F_INPUTS_READY) && ctx->prev_is_scan && !ctx->prev_changes_table && ctx->prev_stream == s &&
                      ctx->group_len > 0 && !overlaps_inflight(ctx->inflight, mine, n_mine);
     if (pipelined) {
@@ -861,7 +862,7 @@ int egpu_bestfit_batches_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K
 
 int egpu_bestfit_batches_shard_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags, uint64_t first_step,
                                    void* stream) {
-    if (!ctx || (flags & ~EGPU_F_INPUTS_READY) || first_step >= (1ull << 47)) return EGPU_ERR_INVALID;
+    if (!ctx || (flags & ~(EGPU_F_INPUTS_READY | EGPU_F_APPLY)) || first_step >= (1ull << 47)) return EGPU_ERR_INVALID;
     const int rc = check_batches(batches, K);
     if (rc != EGPU_OK) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -1159,7 +1160,7 @@ int egpu_table_apply_peers_multi_dev(egpu_ctx* ctx, uint64_t first_step, int nst
     }
     ApplyOuts outs;
     for (int k = 0; k < kApplyMax; ++k) outs.table_out[k] = (d_table_outs && k < nsteps) ? d_table_outs[k] : nullptr;
-    apply_peers_kernel<<<1, kMaxD, 0, s>>>(ctx->d_state, first_step + 1, nsteps, outs, commit);
+    apply_peers_kernel<<<commit ? 1 : nsteps, kMaxD, 0, s>>>(ctx->d_state, first_step + 1, nsteps, outs, commit);
     EGPU_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return EGPU_OK;

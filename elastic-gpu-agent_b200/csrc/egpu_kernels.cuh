@@ -51,6 +51,7 @@ constexpr int kFlagBoundary = 16;     // with kFlagLateWait: group boundary of a
                                       // alongside the predecessors, but wait for them BEFORE the epilogue
                                       // and only then trigger: everything older is complete when the next
                                       // group starts, which bounds the launches in flight
+constexpr int kFlagApplyNow = 32;     // multi-batch sharded launches: the last CTA of a batch also applies that batch's exchange step
 constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before the scan: only on
                                       // streams the caller declared pipelined (EGPU_F_INPUTS_READY)
 
@@ -59,14 +60,22 @@ constexpr int kAccShift = 38;
 
 // Multi-GPU exchange of demand vectors through peer memory.  Every rank owns
 // one XchgBuf (kXchgSlots slots); rank r's demand vector of step s lands in slot s % kXchgSlots, row r, of EVERY
-// rank's buffer (plain stores over NVLink), followed by flag = s + 1 with release.sys.
+// rank's buffer (plain stores over NVLink).  Flag-in-data: every 8-byte word carries 32 bits of
+// payload and a 32-bit tag derived from the step (8-byte stores are single-copy atomic), so the
+// receiver polls the words themselves - no separate flag, no release fence, one NVLink one-way
+// latency from the sender's last store to the receiver seeing a complete vector.  (Round 1 wrote
+// the vector, fenced at system scope and then raised a flag: a fence round trip more.)
 constexpr int kMaxRanks = 8;
-constexpr int kXchgSlots = 256;  // 2.1 MB per rank; a rank's scans may run kXchgSlots / 2 steps ahead of its applies
+constexpr int kXchgSlots = 256;  // 4 MB per rank; a rank's scans may run kXchgSlots / 2 steps ahead of its applies
 struct XchgRow {
-    long long delta[2 * kMaxD];
-    unsigned long long flag;  // step + 1 once delta[] is complete
-    unsigned long long pad_;
+    // value j (core sums 0..D-1, mem sums D..2D-1) = two words: ll[2j] low half, ll[2j+1] high half,
+    // each  tag << 32 | half
+    unsigned long long ll[2 * 2 * kMaxD];
 };
+__host__ __device__ __forceinline__ uint32_t xchg_tag(unsigned long long step_plus1) {
+    // non-zero (a consumed word is 0), and two uses of one slot (steps 256 apart) never share a tag
+    return static_cast<uint32_t>(step_plus1) | 1u;
+}
 struct XchgBuf {
     XchgRow slot[kXchgSlots][kMaxRanks];
     // start gate (egpu_peer_gate_dev): rank r stores its gate epoch into ready[r] of EVERY rank's buffer

@@ -113,6 +113,50 @@ __device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int
         static_cast<unsigned long long>(static_cast<uint32_t>(mem));
 }
 
+// ---- exchange rows (XchgRow): push one device's two sums to every peer, pull and consume ----
+// thread d < D of one CTA; (dc, dm) = this rank's demand on device d under exchange step step_plus1 - 1
+__device__ __forceinline__ void xchg_push(DevState* st, unsigned long long step_plus1, int d, int D, long long dc, long long dm) {
+    const int world = st->peer.world, me = st->peer.rank;
+    const int xs = static_cast<int>((step_plus1 - 1) % kXchgSlots);
+    const unsigned long long tag = static_cast<unsigned long long>(xchg_tag(step_plus1)) << 32;
+    const unsigned long long c = static_cast<unsigned long long>(dc), m = static_cast<unsigned long long>(dm);
+    const ulonglong2 wc = make_ulonglong2(tag | (c & 0xffffffffull), tag | (c >> 32));
+    const ulonglong2 wm = make_ulonglong2(tag | (m & 0xffffffffull), tag | (m >> 32));
+    for (int p = 0; p < world; ++p) {
+        XchgRow& row = st->peer.buf[p]->slot[xs][me];
+        // two 16-byte stores (each half is an 8-byte single-copy-atomic word with its own tag)
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&row.ll[2 * d]), "l"(wc.x), "l"(wc.y) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&row.ll[2 * (D + d)]), "l"(wm.x), "l"(wm.y) : "memory");
+    }
+}
+// thread d < D: waits until rank g's two values for device d carry the step's tag, for every rank g
+// of the world; adds those of ranks [g_lo, g_hi) into (dc, dm); zeroes the words (consumed: a replayed
+// sequence pushes the same steps again).  false = gave up after ~2 s (a rank died).
+__device__ __forceinline__ bool xchg_pull(XchgRow* rows, int world, unsigned long long step_plus1, int d, int D, int g_lo, int g_hi,
+                                          long long& dc, long long& dm) {
+    const unsigned long long tag = xchg_tag(step_plus1);
+    const long long t0 = clock64();
+    for (int g = 0; g < world; ++g) {
+        unsigned long long* pc = &rows[g].ll[2 * d];
+        unsigned long long* pm = &rows[g].ll[2 * (D + d)];
+        unsigned long long c0, c1, m0, m1;
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(pc) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(m0), "=l"(m1) : "l"(pm) : "memory");
+            if ((c0 >> 32) == tag && (c1 >> 32) == tag && (m0 >> 32) == tag && (m1 >> 32) == tag) break;
+            if (clock64() - t0 > 4000000000ll) return false;
+            __nanosleep(40);
+        }
+        if (g >= g_lo && g < g_hi) {
+            dc += static_cast<long long>((c0 & 0xffffffffull) | (c1 << 32));
+            dm += static_cast<long long>((m0 & 0xffffffffull) | (m1 << 32));
+        }
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pc), "l"(0ull) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pm), "l"(0ull) : "memory");
+    }
+    return true;
+}
+
 // Where a CTA's epilogue goes: the launch's (or, in a multi-batch launch, the batch's) slot of
 // running sums + arrival ticket, the exchange step to push under, and which of how many CTAs
 // of that batch this one is.
@@ -121,6 +165,7 @@ struct EpiCtl {
     unsigned long long push;  // step + 1 when the demand vector must also go to the peers' exchange buffers, else 0
     unsigned int lag;         // with push: also apply the exchanged vectors of step (step - lag) here
     int tile, n_tiles;        // this CTA's number among the CTAs that share `ep`
+    bool apply_now;           // with push: wait for the peers' vectors of THIS step here and write its table'
 };
 // Single-batch launches carry it as one word: bits 0..7 = epilogue slot, bits 8..55 = step + 1
 // (0 = single GPU), bits 56..63 = lag; the CTAs of the grid are the tiles.
@@ -131,6 +176,7 @@ __device__ __forceinline__ EpiCtl epi_from_word(DevState* st, unsigned long long
     ec.lag = static_cast<unsigned int>(slot_step >> 56);
     ec.tile = static_cast<int>(blockIdx.x);
     ec.n_tiles = static_cast<int>(gridDim.x);
+    ec.apply_now = false;
     return ec;
 }
 
@@ -186,18 +232,8 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
             delta_out[tid] = dc;
             delta_out[D + tid] = dm;
         }
-        if (push) {  // fused exchange: this rank's vector straight into every rank's buffer
-            const int world = st->peer.world, me = st->peer.rank;
-            const int xs = static_cast<int>((push - 1) % kXchgSlots);
-            for (int p = 0; p < world; ++p) {
-                XchgRow& row = st->peer.buf[p]->slot[xs][me];
-                row.delta[tid] = dc;
-                row.delta[D + tid] = dm;
-            }
-            // no fence here: the barrier below orders these stores before the flag stores of
-            // other threads, and st.release.sys is cumulative over what its thread has observed
-        }
-        if (table_out && !lag) {
+        if (push) xchg_push(st, push, tid, D, dc, dm);  // fused exchange: this rank's vector straight into every rank's buffer
+        if (table_out && !lag && !ec.apply_now) {
             table_out[tid] = sat_i32(nc);
             table_out[D + tid] = sat_i32(nm);
             table_out[2 * D + tid] = over;
@@ -215,55 +251,27 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         }
     }
     if (commit) resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
-    if (push) {
-        __syncthreads();  // delta stores happen-before the release stores below
+    if (push && (ec.apply_now || (lag && push > lag))) {
+        // Lagged apply, fused: the vectors of step (step - lag) have had `lag` launches to
+        // arrive, so this wait normally falls through.  It is also the back-pressure that
+        // keeps every rank within `lag` steps of the slowest one (and so inside the slots).
+        // apply_now (multi-batch sharded launches): the same for THIS step - the ranks run the
+        // same launch at the same time (start gate), so the wait is a peer-store latency; this
+        // CTA has pushed before it waits and no rank's push waits for anything, so there is no cycle.
+        const unsigned long long ap = ec.apply_now ? push : push - lag;  // step + 1 of the vectors to apply
         const int world = st->peer.world, me = st->peer.rank;
-        if (tid < world) {
-            unsigned long long* f = &st->peer.buf[tid]->slot[(push - 1) % kXchgSlots][me].flag;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(push) : "memory");
-        }
-        if (lag && push > lag) {
-            // Lagged apply, fused: the vectors of step (step - lag) have had `lag` launches to
-            // arrive, so this spin normally falls through.  It is also the back-pressure that
-            // keeps every rank within `lag` steps of the slowest one (and so inside the slots).
-            const unsigned long long ap = push - lag;  // (step - lag) + 1
-            XchgRow* rows = st->peer.buf[me]->slot[(ap - 1) % kXchgSlots];
-            if (tid == 0) *sLast = 1;
-            __syncthreads();
-            if (tid < world) {
-                unsigned long long f = 0;
-                const long long t0 = clock64();
-                for (;;) {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[tid].flag) : "memory");
-                    if (f == ap) break;
-                    if (clock64() - t0 > 4000000000ll) {
-                        *sLast = 0;
-                        break;
-                    }
-                    __nanosleep(100);
-                }
-            }
-            __syncthreads();
-            if (!*sLast) {
-                if (tid == 0) st->peer_timeout = ap;
-            } else {
-                long long dc = 0, dm = 0;
-                if (tid < D) {
-                    for (int g = 0; g < world; ++g) {
-                        dc += rows[g].delta[tid];
-                        dm += rows[g].delta[D + tid];
-                    }
-                }
-                __syncthreads();
-                if (tid < world) rows[tid].flag = 0ull;  // consumed (a replayed graph reuses step numbers)
-                if (tid < D && table_out) {
-                    const long long nc = static_cast<long long>(st->free_core[tid]) - dc;
-                    const long long nm = static_cast<long long>(st->free_mem[tid]) - dm;
-                    table_out[tid] = sat_i32(nc);
-                    table_out[D + tid] = sat_i32(nm);
-                    table_out[2 * D + tid] = (nc < 0 || nm < 0) ? 1 : 0;
-                }
-            }
+        XchgRow* rows = st->peer.buf[me]->slot[(ap - 1) % kXchgSlots];
+        long long dc = 0, dm = 0;
+        bool ok = true;
+        if (tid < D) ok = xchg_pull(rows, world, ap, tid, D, 0, world, dc, dm);
+        if (!ok) {
+            st->peer_timeout = ap;
+        } else if (tid < D && table_out) {
+            const long long nc = static_cast<long long>(st->free_core[tid]) - dc;
+            const long long nm = static_cast<long long>(st->free_mem[tid]) - dm;
+            table_out[tid] = sat_i32(nc);
+            table_out[D + tid] = sat_i32(nm);
+            table_out[2 * D + tid] = (nc < 0 || nm < 0) ? 1 : 0;
         }
     }
     if (tid == 0) ep.ticket = 0u;
@@ -468,6 +476,7 @@ bestfit_sorted_multi_kernel(DevState* __restrict__ st, const __grid_constant__ M
     ec.lag = 0;
     ec.tile = tile_i;
     ec.n_tiles = tiles;
+    ec.apply_now = (flags & kFlagApplyNow) != 0;
     snapshot_epilogue<DT, THREADS>(s, st, D, b.delta, b.table_out, flags, ec);
     if (late && !boundary) pdl_wait();
 }
@@ -1014,6 +1023,7 @@ bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ Mult
     ec.lag = 0;
     ec.tile = tile_i;
     ec.n_tiles = tiles;
+    ec.apply_now = (flags & kFlagApplyNow) != 0;
     epilogue_publish<THREADS / 32>(&sm.sWarpAcc[0][0], 2 * kMaxD, 0, kMaxD, sm.sFc, sm.sFm, sm.sPosDev, &sm.sLast, st, D,
                                    b.delta, b.table_out, flags, ec);
     if (late && !boundary) pdl_wait();
@@ -1104,6 +1114,10 @@ gate_kernel(DevState* __restrict__ st, const unsigned long long* __restrict__ ho
     }
 }
 
+// Without commit the steps are independent of each other (each is table - its own sum): the grid
+// has one CTA per step, so the waits overlap instead of queueing behind one another (the vectors of
+// all the steps of a multi-batch launch arrive at about the same time, when that launch drains).
+// With commit the steps apply on top of each other: one CTA walks them in order.
 __global__ void __launch_bounds__(kMaxD)
 apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus1, int nsteps, ApplyOuts outs, int commit) {
     __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
@@ -1114,41 +1128,20 @@ apply_peers_kernel(DevState* __restrict__ st, unsigned long long first_step_plus
     // running table across the steps of this launch (only installed when commit is set)
     long long cur_c = d < D ? st->free_core[d] : 0, cur_m = d < D ? st->free_mem[d] : 0;
     int32_t sticky = 0;
-    for (int k = 0; k < nsteps; ++k) {
+    const int k_begin = commit ? 0 : static_cast<int>(blockIdx.x);
+    const int k_end = commit ? nsteps : k_begin + 1;
+    for (int k = k_begin; k < k_end; ++k) {
         const unsigned long long step_plus1 = first_step_plus1 + k;
         XchgRow* rows = st->peer.buf[me]->slot[(step_plus1 - 1) % kXchgSlots];
         if (d == 0) sOk = 1;
         __syncthreads();
-        if (d < world) {
-            unsigned long long f = 0;
-            const long long t0 = clock64();
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[d].flag) : "memory");
-                if (f == step_plus1) break;
-                if (clock64() - t0 > 4000000000ll) {
-                    sOk = 0;
-                    break;
-                }
-                __nanosleep(100);
-            }
-        }
+        long long dc = 0, dm = 0;
+        if (d < D && !xchg_pull(rows, world, step_plus1, d, D, 0, world, dc, dm)) sOk = 0;
         __syncthreads();
         if (!sOk) {
             if (d == 0) st->peer_timeout = step_plus1;
             return;
         }
-        long long dc = 0, dm = 0;
-        if (d < D) {
-            for (int g = 0; g < world; ++g) {
-                dc += rows[g].delta[d];
-                dm += rows[g].delta[D + d];
-            }
-        }
-        __syncthreads();
-        // consume the flags: a replayed CUDA graph pushes the same step numbers again, and a
-        // stale flag must not look like the new one.  (The slot is not written again before
-        // this rank has applied 16 more steps, see the header.)
-        if (d < world) rows[d].flag = 0ull;
         if (d < D) {
             const long long nc = cur_c - dc, nm = cur_m - dm;
             const int32_t over = (nc < 0 || nm < 0) ? 1 : 0;
@@ -1392,19 +1385,9 @@ prefix_base_kernel(DevState* __restrict__ st, unsigned long long step_plus1, lon
     XchgRow* rows = st->peer.buf[me]->slot[(step_plus1 - 1) % kXchgSlots];
     if (d == 0) sOk = 1;
     __syncthreads();
-    if (d < world) {  // all ranks, not only the lower ones: the flags are consumed below
-        unsigned long long f = 0;
-        const long long t0 = clock64();
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&rows[d].flag) : "memory");
-            if (f == step_plus1) break;
-            if (clock64() - t0 > 4000000000ll) {
-                sOk = 0;
-                break;
-            }
-            __nanosleep(100);
-        }
-    }
+    long long bc = 0, bm = 0;
+    // waits for all ranks (every vector is consumed), sums the lower ones
+    if (d < D && !xchg_pull(rows, world, step_plus1, d, D, 0, me, bc, bm)) sOk = 0;
     __syncthreads();
     if (!sOk) {  // a rank died: defer everything here (base beyond any capacity) and record it
         if (d == 0) st->peer_timeout = step_plus1;
@@ -1412,17 +1395,8 @@ prefix_base_kernel(DevState* __restrict__ st, unsigned long long step_plus1, lon
         base[kMaxD + d] = 1ll << 40;
         return;
     }
-    long long bc = 0, bm = 0;
-    if (d < D) {
-        for (int g = 0; g < me; ++g) {
-            bc += rows[g].delta[d];
-            bm += rows[g].delta[D + d];
-        }
-    }
     base[d] = bc;
     base[kMaxD + d] = bm;
-    __syncthreads();
-    if (d < world) rows[d].flag = 0ull;  // consumed (a replayed CUDA graph pushes the same step again)
 }
 
 // This rank's COMMITTED demand (after the cut) to every peer as exchange step `step`;
@@ -1432,24 +1406,13 @@ prefix_push_kernel(DevState* __restrict__ st, const PrefixOut* __restrict__ pf, 
                    long long* __restrict__ delta_out) {
     const int D = st->D;
     const int d = threadIdx.x;
-    const int world = st->peer.world, me = st->peer.rank;
-    const int xs = static_cast<int>((step_plus1 - 1) % kXchgSlots);
     if (d < D) {
         const long long dc = pf->committed_c[d], dm = pf->committed_m[d];
         if (delta_out) {
             delta_out[d] = dc;
             delta_out[D + d] = dm;
         }
-        for (int p = 0; p < world; ++p) {
-            XchgRow& row = st->peer.buf[p]->slot[xs][me];
-            row.delta[d] = dc;
-            row.delta[D + d] = dm;
-        }
-    }
-    __syncthreads();  // the vector stores happen-before the release stores of the flags
-    if (d < world) {
-        unsigned long long* f = &st->peer.buf[d]->slot[xs][me].flag;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(step_plus1) : "memory");
+        xchg_push(st, step_plus1, d, D, dc, dm);
     }
 }
 

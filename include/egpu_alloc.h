@@ -99,6 +99,12 @@ extern "C" {
                                     Single GPU; not with EGPU_VARIANT_GRID.  In egpu_bestfit_batch
                                     pass it in `commit` (EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT). */
 
+#define EGPU_F_APPLY         8   /* egpu_bestfit_batches_shard_dev only: the last CTA of every batch, having pushed the
+                                    batch's demand vector, also waits for the peers' vectors of that exchange step and
+                                    writes table' (= table - sum over ranks) to the batch's d_table_out: no apply call,
+                                    no second stream.  Never commits.  Every rank must issue the same launch; start the
+                                    ranks together (egpu_peer_gate_dev) or the wait is as long as their skew. */
+
 /* kernel variants for the snapshot scan (egpu_set_variant) */
 #define EGPU_VARIANT_AUTO    0   /* SORTED for D <= 16, LUT above */
 #define EGPU_VARIANT_GRID    1   /* direct (device x request) score grid, min over packed keys */
@@ -268,8 +274,9 @@ int egpu_bestfit_batch_shard_dev(egpu_ctx* ctx, const int32_t* d_req_core,
 int egpu_table_apply_peers_dev(egpu_ctx* ctx, uint64_t step, int32_t* d_table_out,
                                int commit, void* stream);
 /* K sharded steps in one launch: batch k is exchange step first_step + k (egpu_bestfit_batches_dev
- * + the fused push of egpu_bestfit_batch_shard_dev); d_table_out of the batches is ignored
- * (table' comes from the apply calls). */
+ * + the fused push of egpu_bestfit_batch_shard_dev).  Without EGPU_F_APPLY d_table_out of the
+ * batches is ignored (table' comes from the apply calls); with it the exchange steps are consumed
+ * by the launch itself and no apply call must follow. */
 int egpu_bestfit_batches_shard_dev(egpu_ctx* ctx, const egpu_batch* batches, int32_t K, int flags,
                                    uint64_t first_step, void* stream);
 /* Start gate for a sharded sequence.  egpu_peer_gate_dev enqueues a one-warp kernel that

@@ -337,8 +337,10 @@ def test_sharded_step_world1_equals_snapshot(name, alloc, oracle_c, egpu):
 
 # ---- sharded multi-batch launches + start gate, world = 1 (world = 2: test_gpu_peer_exchange.py) ----
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", ["cfg3", "cfg4"])
-def test_world1_sharded_multi_batch_and_gate(name, alloc, oracle_c, egpu):
+def test_world1_sharded_multi_batch_and_gate(name, fused, alloc, oracle_c, egpu):
+    """fused = EGPU_F_APPLY: the batch's own last CTA applies its exchange step; otherwise one apply launch."""
     import torch
     w = egpu.synth.workload(name)
     D = int(w["D"])
@@ -350,13 +352,18 @@ def test_world1_sharded_multi_batch_and_gate(name, alloc, oracle_c, egpu):
     with torch.cuda.stream(st):
         host, tens, tup = _dev_batches(torch, egpu, w["dist"], range(50, 50 + K), rows, D)
     torch.cuda.synchronize()
-    alloc.gate_dev(st.cuda_stream)
-    alloc.bestfit_batches_shard_dev(tup, first, st.cuda_stream, inputs_ready=True)
-    alloc.apply_peers_multi_dev(first, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
-    alloc.gate_open()
-    torch.cuda.synchronize()
-    assert alloc.peer_last_timeout == 0
-    _check_batches(oracle_c, w, host, tens, rows, D)
+    for rep in range(2):  # the second pass reuses the same exchange steps: the first must have consumed its flags
+        alloc.gate_dev(st.cuda_stream)
+        alloc.bestfit_batches_shard_dev(tup, first, st.cuda_stream, inputs_ready=True, apply=fused)
+        if not fused:
+            alloc.apply_peers_multi_dev(first, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
+        alloc.gate_open()
+        torch.cuda.synchronize()
+        assert alloc.peer_last_timeout == 0
+        _check_batches(oracle_c, w, host, tens, rows, D)
+        for t in tens:
+            t[4].fill_(-7)
+        torch.cuda.synchronize()
     alloc.peer_detach()
 
 

@@ -167,7 +167,7 @@ def test_world2_two_processes_one_gpu(lag, oracle_c, egpu):
         assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
 
 
-def _multi_rank_main(rank, world, conn, peer_conn, K, R, replays):
+def _multi_rank_main(rank, world, conn, peer_conn, K, R, replays, fused):
     """cfg4 (D = 64) row-sharded: every replay is gate -> one multi-batch launch of K sharded steps
     -> apply launches on a second stream, the shape bench.py --gpus N captures in a CUDA graph."""
     sys.path.insert(0, ROOT)
@@ -194,15 +194,16 @@ def _multi_rank_main(rank, world, conn, peer_conn, K, R, replays):
             dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
             tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
             tens.append((c, m, idx, dl, tab))
-            tup.append((c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), 0))
+            tup.append((c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), tab.data_ptr()))
     torch.cuda.synchronize()
     batches = a.make_batches(tup)
     for rep in range(replays):
         # step numbers restart at 0 on every replay (as a replayed CUDA graph does): the apply
         # kernels consumed the flags, and the ranks are synchronised between replays
         a.gate_dev(st.cuda_stream)
-        a.bestfit_batches_shard_dev(batches, 0, st.cuda_stream, inputs_ready=True)
-        a.apply_peers_multi_dev(0, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
+        a.bestfit_batches_shard_dev(batches, 0, st.cuda_stream, inputs_ready=True, apply=fused)
+        if not fused:
+            a.apply_peers_multi_dev(0, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
         a.gate_open()
         torch.cuda.synchronize()
         peer_conn.send("replayed")
@@ -215,9 +216,11 @@ def _multi_rank_main(rank, world, conn, peer_conn, K, R, replays):
     a.close()
 
 
-def test_world2_cfg4_sharded_multi_batch_with_gate(oracle_c, egpu):
+@pytest.mark.parametrize("fused", [False, True])
+def test_world2_cfg4_sharded_multi_batch_with_gate(fused, oracle_c, egpu):
     """BASELINE config 4's shape (64 devices, request rows sharded over the ranks) at world = 2:
-    lookup scan + fused peer push out of a multi-batch launch, start gate, batched apply."""
+    lookup scan + fused peer push out of a multi-batch launch, start gate; table' from a batched
+    apply launch or (fused = EGPU_F_APPLY) from the last CTA of every batch."""
     import torch.multiprocessing as mp
     from elastic_gpu_agent_b200 import sharding
     ctx = mp.get_context("spawn")
@@ -225,8 +228,8 @@ def test_world2_cfg4_sharded_multi_batch_with_gate(oracle_c, egpu):
     a_conn, b_conn = ctx.Pipe()
     res0_r, res0_w = ctx.Pipe(False)
     res1_r, res1_w = ctx.Pipe(False)
-    p0 = ctx.Process(target=_multi_rank_main, args=(0, 2, res0_w, a_conn, K, R, 3))
-    p1 = ctx.Process(target=_multi_rank_main, args=(1, 2, res1_w, b_conn, K, R, 3))
+    p0 = ctx.Process(target=_multi_rank_main, args=(0, 2, res0_w, a_conn, K, R, 3, fused))
+    p1 = ctx.Process(target=_multi_rank_main, args=(1, 2, res1_w, b_conn, K, R, 3, fused))
     p0.start()
     p1.start()
     assert res0_r.poll(180) and res1_r.poll(180), "ranks did not finish"
