@@ -709,6 +709,22 @@ def main():
                            8 * e2e_R, 4 * e2e_R + 16 * D, "egpu_bestfit_batch (C ABI, pageable host buffers: staged through HBM)", exchange=False)
     if R <= (1 << 20):
         e2e_pageable["parity_vs_oracle"] = bool(np.array_equal(page_idx, exp_last))
+    # the same caller-owned buffers after egpu_host_register: pinned in place, no staging (registration not timed: it is
+    # done once for buffers a caller keeps)
+    e2e_registered = None
+    try:
+        reg = [page_idx, pdc, pdm] + [host[b][k] for b in range(nhb) for k in (3, 4)]
+        for a_ in reg:
+            alloc.host_register(a_)
+        e2e_registered = e2e_leg(lambda b: alloc.bestfit_raw(host[b][3].ctypes.data, host[b][4].ctypes.data, e2e_R, page_idx.ctypes.data,
+                                                             pdc.ctypes.data, pdm.ctypes.data),
+                                 8 * e2e_R, 4 * e2e_R + 16 * D, "egpu_bestfit_batch on caller-owned buffers pinned by egpu_host_register", exchange=False)
+        if R <= (1 << 20):
+            e2e_registered["parity_vs_oracle"] = bool(np.array_equal(page_idx, exp_last))
+        for a_ in reg:
+            alloc.host_unregister(a_)
+    except Exception as ex:  # registration can be refused (locked-memory limits): report, do not fail the run
+        e2e_registered = {"unavailable": str(ex)}
     # packed wire format (4 bytes in, 1 byte out per decision): PCIe, not the scan, bounds e2e
     ph = []
     for b in range(nhb):
@@ -800,6 +816,7 @@ def main():
                        "parallelism": f"request rows sharded over {world} GPU(s), table replicated"},
             "e2e": e2e,
             "e2e_pageable": e2e_pageable,
+            "e2e_registered": e2e_registered,
             "e2e_packed": e2e_packed,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -93,6 +93,8 @@ def load() -> C.CDLL:
         "egpu_bestfit_batch_packed_dev": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int, vp]),
         "egpu_host_alloc": (C.c_int, [vp, C.POINTER(vp), C.c_int64]),
         "egpu_host_free": (None, [vp, vp]),
+        "egpu_host_register": (C.c_int, [vp, vp, C.c_int64]),
+        "egpu_host_unregister": (C.c_int, [vp, vp]),
         "egpu_bestfit_batch_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int, vp]),
         "egpu_table_apply_deltas_dev": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp]),
         "egpu_synth_requests_dev": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, vp, vp, vp]),

@@ -194,6 +194,13 @@ class BestFitAllocator:
     def host_free(self, addr: int):
         self._lib.egpu_host_free(self._h, C.c_void_p(addr))
 
+    def host_register(self, arr: np.ndarray):
+        """egpu_host_register on a caller-owned numpy array (stays pinned until host_unregister)."""
+        self._check(self._lib.egpu_host_register(self._h, C.c_void_p(arr.ctypes.data), int(arr.nbytes)), "egpu_host_register")
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self._lib.egpu_host_unregister(self._h, C.c_void_p(arr.ctypes.data)), "egpu_host_unregister")
+
     def pinned_array(self, n: int, dtype=np.int32) -> np.ndarray:
         """numpy view over pinned host memory owned by the context (freed with it
         only if the caller calls host_free(arr.ctypes.data))."""

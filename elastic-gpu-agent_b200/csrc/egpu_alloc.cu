@@ -821,6 +821,23 @@ void egpu_host_free(egpu_ctx* ctx, void* p) {
     (void)cudaGetLastError();
 }
 
+int egpu_host_register(egpu_ctx* ctx, void* p, int64_t bytes) {
+    if (!ctx || !p || bytes <= 0) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    EGPU_CUDA(ctx, cudaHostRegister(p, static_cast<size_t>(bytes), cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return EGPU_OK;
+}
+
+int egpu_host_unregister(egpu_ctx* ctx, void* p) {
+    if (!ctx || !p) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    EGPU_CUDA(ctx, cudaSetDevice(ctx->dev));
+    EGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nothing of ours may still be reading it
+    EGPU_CUDA(ctx, cudaHostUnregister(p));
+    return EGPU_OK;
+}
+
 int egpu_bestfit_batch_dev(egpu_ctx* ctx, const int32_t* d_req_core, const int32_t* d_req_mem, int64_t R,
                            int32_t* d_out_idx, int64_t* d_delta, int32_t* d_table_out, int flags,
                            void* stream) {

@@ -12,6 +12,10 @@ namespace {
 std::vector<int32_t> g_fc, g_fm;
 int32_t g_req_core = -1, g_req_mem = -1, g_answer = -1;
 int g_sets = 0, g_scans = 0;
+// optional: instead of the scripted answer, ask a callback the TEST installs (tests/test_kubelet_grpc.py
+// passes the oracle's oracle_pick_one - test infrastructure answering for the device, never the product)
+using pick_fn = int32_t (*)(const int32_t*, const int32_t*, int32_t, int32_t, int32_t);
+pick_fn g_pick = nullptr;
 }  // namespace
 
 extern "C" {
@@ -25,9 +29,11 @@ int egpu_bestfit_query(egpu_ctx*, const int32_t* free_core, const int32_t* free_
     g_req_core = req_core[0];
     g_req_mem = req_mem[0];
     g_scans += 1;
-    out_idx[0] = g_answer;
+    out_idx[0] = g_pick ? g_pick(free_core, free_mem, D, req_core[0], req_mem[0]) : g_answer;
     return EGPU_OK;
 }
+
+void stub_use_callback(pick_fn f) { g_pick = f; }
 
 void stub_script_answer(int32_t idx) { g_answer = idx; }
 int32_t stub_table(int32_t* fc, int32_t* fm) {

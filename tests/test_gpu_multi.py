@@ -381,3 +381,35 @@ def test_gate_unattached_waits_for_the_host(alloc, egpu):
     alloc.gate_open()
     st.synchronize()
     assert int(flag.item()) == 1 and alloc.peer_last_timeout == 0
+
+
+def test_registered_caller_memory_takes_the_zero_copy_path(alloc, oracle_c, egpu):
+    """egpu_host_register: plain caller memory pinned in place; the same call then runs as one launch that
+    reads and writes it across PCIe (no staging copies), and the answers are the same."""
+    w = egpu.synth.workload("cfg3")
+    R = 200_003
+    rc, rm = egpu.synth.requests(3, 21, R)
+    # page-aligned caller buffers (what C.malloc / mmap give a cgo caller for a large slice)
+    def aligned(n):
+        raw = np.empty(n * 4 + 4096, dtype=np.uint8)
+        off = (-raw.ctypes.data) % 4096
+        return raw[off:off + n * 4].view(np.int32), raw
+    c, _k1 = aligned(R)
+    m, _k2 = aligned(R)
+    i, _k3 = aligned(R)
+    c[:], m[:] = rc, rm
+    o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm, 4)
+    alloc.set_table(w["free_core"], w["free_mem"])
+    dc, dm = np.zeros(8, np.int64), np.zeros(8, np.int64)
+    alloc.bestfit_raw(c.ctypes.data, m.ctypes.data, R, i.ctypes.data, dc.ctypes.data, dm.ctypes.data)   # pageable: staged
+    assert np.array_equal(i, o_idx)
+    for a in (c, m, i):
+        alloc.host_register(a)
+    i[:] = -9
+    alloc.bestfit_raw(c.ctypes.data, m.ctypes.data, R, i.ctypes.data, dc.ctypes.data, dm.ctypes.data)   # registered: in place
+    assert np.array_equal(i, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
+    for a in (c, m, i):
+        alloc.host_unregister(a)
+    i[:] = -9
+    alloc.bestfit_raw(c.ctypes.data, m.ctypes.data, R, i.ctypes.data, dc.ctypes.data, dm.ctypes.data)   # staged again
+    assert np.array_equal(i, o_idx)
