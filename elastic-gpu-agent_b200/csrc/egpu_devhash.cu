@@ -360,6 +360,99 @@ __global__ void sha256_sets_kernel(unsigned char* __restrict__ msg, const unsign
     o[0] = h0; o[1] = h1; o[2] = h2; o[3] = h3; o[4] = h4; o[5] = h5; o[6] = h6; o[7] = h7;
 }
 
+// ---- SHA-256 of LONG messages: one CTA (two warps) per message -------------------------
+// The compression chain of one message is serial (block k needs the state after block k - 1), so a
+// node-scale batch - ~100 sets of 4 K .. 16 K IDs, 0.5 .. 2 K blocks each - is bound by the latency
+// of the longest chain, not by throughput.  What can be taken off the chain is: the loads, the
+// byte swaps and the whole message schedule W[16..63] (48 of the 64 rounds' extra work), and the
+// additions of the round constants.  Warp 1 does all of that for 32 blocks at a time (lane = block)
+// into a shared-memory ring of K[i] + W[i] words; lane 0 of warp 0 walks the blocks in order with
+// nothing but the 64 rounds left: per round the dependent path is three instructions
+// (rotations -> xor -> 3-input add).  Double-buffered, one __syncthreads per 32 blocks.
+constexpr int kShaGroup = 32;
+__global__ void __launch_bounds__(64)
+sha256_long_kernel(unsigned char* __restrict__ msg, const unsigned long long* __restrict__ msg_base,
+                   const unsigned long long* __restrict__ msg_len, long long n_sets, uint32_t* __restrict__ digest) {
+    __shared__ uint32_t kw[2][kShaGroup][64];  // 16 KB: K[i] + W[i] of 2 x 32 blocks
+    const long long s = blockIdx.x;
+    if (s >= n_sets) return;
+    unsigned char* m = msg + msg_base[s];
+    const unsigned long long len = msg_len[s];
+    const unsigned long long total = ((len + 8) / 64 + 1) * 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // padding in place (the layout reserved the room), by the whole CTA
+    for (unsigned long long i = len + tid; i < total; i += 64) {
+        unsigned char v = 0;
+        if (i == len) v = 0x80;
+        else if (i >= total - 8) v = static_cast<unsigned char>((len * 8) >> (8 * (total - 1 - i)));
+        m[i] = v;
+    }
+    __syncthreads();
+    const unsigned long long n_blk = total / 64;
+    const uint4* words = reinterpret_cast<const uint4*>(m);  // 64-byte aligned base
+    auto produce = [&](unsigned long long g) {  // warp 1: schedule of blocks g*32 .. g*32+31 into buffer g & 1
+        const unsigned long long blk = g * kShaGroup + lane;
+        if (blk >= n_blk) return;
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = words[blk * 4 + q];
+            w[4 * q] = __byte_perm(v.x, 0, 0x0123);
+            w[4 * q + 1] = __byte_perm(v.y, 0, 0x0123);
+            w[4 * q + 2] = __byte_perm(v.z, 0, 0x0123);
+            w[4 * q + 3] = __byte_perm(v.w, 0, 0x0123);
+        }
+        uint32_t* out = kw[g & 1][lane];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            uint32_t wi;
+            if (i < 16) {
+                wi = w[i];
+            } else {
+                const uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+                const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+                w[i & 15] = wi;
+            }
+            // column-rotated so that the 32 lanes (rows of 64 words = the same bank) do not all hit one bank
+            out[(i + lane) & 63] = wi + kSha[i];
+        }
+    };
+    uint32_t h0 = 0x6a09e667, h1 = 0xbb67ae85, h2 = 0x3c6ef372, h3 = 0xa54ff53a, h4 = 0x510e527f, h5 = 0x9b05688c,
+             h6 = 0x1f83d9ab, h7 = 0x5be0cd19;
+    const unsigned long long n_grp = (n_blk + kShaGroup - 1) / kShaGroup;
+    if (warp == 1) produce(0);
+    __syncthreads();
+    for (unsigned long long g = 0; g < n_grp; ++g) {
+        if (warp == 1) {
+            if (g + 1 < n_grp) produce(g + 1);
+        } else if (lane == 0) {
+            const unsigned long long b_end = (g + 1) * kShaGroup < n_blk ? kShaGroup : n_blk - g * kShaGroup;
+            for (int bi = 0; bi < static_cast<int>(b_end); ++bi) {
+                const uint32_t* x = kw[g & 1][bi];
+                uint32_t a = h0, b = h1, c = h2, d = h3, e = h4, f = h5, gg = h6, h = h7;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const uint32_t t0 = h + x[(i + bi) & 63];          // off the dependent path
+                    const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+                    const uint32_t ch = (e & f) ^ (~e & gg);
+                    const uint32_t t1 = t0 + S1 + ch;
+                    const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+                    const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+                    h = gg; gg = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+                }
+                h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; h5 += f; h6 += gg; h7 += h;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t* o = digest + s * 8;
+        o[0] = h0; o[1] = h1; o[2] = h2; o[3] = h3; o[4] = h4; o[5] = h5; o[6] = h6; o[7] = h7;
+    }
+}
+
 // Device.Equals against set 0: one thread per candidate ID compares with the request's ID
 // at the same sorted rank; any difference clears the candidate's flag
 __global__ void locate_compare_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ set,
@@ -515,9 +608,16 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
                                                 r.msg_base.as<unsigned long long>(), r.msg.as<unsigned char>());
             ctx->launches += 1;
         }
-        sha256_sets_kernel<<<static_cast<unsigned>((n_sets + 63) / 64), 64, 0, s>>>(
-            r.msg.as<unsigned char>(), r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>(), n_sets,
-            r.digest.as<uint32_t>());
+        // few long messages (node-scale Locate: sets of thousands of IDs): one CTA per message, schedule and
+        // loads off the chain; many short ones (one Allocate's worth of IDs each): one message per thread
+        if (n_sets <= 8192 && n_ids / n_sets >= 256)
+            sha256_long_kernel<<<static_cast<unsigned>(n_sets), 64, 0, s>>>(
+                r.msg.as<unsigned char>(), r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>(), n_sets,
+                r.digest.as<uint32_t>());
+        else
+            sha256_sets_kernel<<<static_cast<unsigned>((n_sets + 63) / 64), 64, 0, s>>>(
+                r.msg.as<unsigned char>(), r.msg_base.as<unsigned long long>(), r.msg_len.as<unsigned long long>(), n_sets,
+                r.digest.as<uint32_t>());
         ctx->launches += 1;
         EGPU_CUDA(ctx, cudaGetLastError());
     }

@@ -19,6 +19,10 @@
 #include <map>
 #include <string>
 #include <utility>
+#include <atomic>
+#include <thread>
+#include <cstdlib>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/egpu_restore.h"
@@ -377,20 +381,63 @@ extern "C" int egpu_table_restore(egpu_ctx* ctx, const char* const* keys, const 
         v[static_cast<size_t>(ord)] = gpu;
     }
 
+    // Phase 1, parallel over records: key check + JSON parse (the reader is most of the host time of a
+    // node-scale restore: ~10 MB of record values).  Each record parses into its own slot; the merge
+    // below walks the slots in record order, so results and the first reported error are those of a
+    // sequential pass.
+    for (int64_t r = 0; r < n_records; ++r)
+        if (!keys[r] || key_lens[r] < 0 || val_lens[r] < 0 || (val_lens[r] > 0 && !vals[r])) return EGPU_ERR_INVALID;
+    std::vector<std::vector<Entry>> parsed(static_cast<size_t>(n_records));
+    std::vector<signed char> perr(static_cast<size_t>(n_records), 0);  // 1 = bad key, 2 = bad value
+    {
+        int64_t bytes = 0;
+        for (int64_t r = 0; r < n_records; ++r) bytes += val_lens[r];
+        int nthr = 1;
+        if (const char* e = std::getenv("EGPU_RESTORE_THREADS")) nthr = std::atoi(e);
+        else nthr = static_cast<int>(std::min<int64_t>(std::min<int64_t>(8, std::thread::hardware_concurrency()), bytes >> 18));  // >= 256 KB per thread
+        if (nthr > n_records) nthr = static_cast<int>(n_records);
+        if (nthr < 1) nthr = 1;
+        std::atomic<int64_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const int64_t r = next.fetch_add(1, std::memory_order_relaxed);
+                if (r >= n_records) return;
+                // strings.Split(key, "/") must give exactly two parts (pkg/types/pod.go:40-43)
+                int64_t slashes = 0;
+                for (int64_t i = 0; i < key_lens[r]; ++i) slashes += keys[r][i] == '/';
+                if (slashes != 1) {
+                    perr[static_cast<size_t>(r)] = 1;
+                    continue;
+                }
+                Json js(vals[r], val_lens[r]);
+                if (!js.parse_record(parsed[static_cast<size_t>(r)])) perr[static_cast<size_t>(r)] = 2;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+    }
+
     std::vector<char> flat;
     std::vector<int64_t> id_off{0}, set_off{0}, link_off{0};
     std::vector<char> hash8;
     std::vector<int32_t> resource, link_gpu;
     std::vector<int64_t> set_record;
+    {
+        size_t id_bytes = 0, n_id = 0;
+        for (const std::vector<Entry>& es : parsed)
+            for (const Entry& e : es) {
+                id_bytes += e.ids.size();
+                n_id += e.ends.size();
+            }
+        flat.reserve(id_bytes);
+        id_off.reserve(n_id + 1);
+    }
     for (int64_t r = 0; r < n_records; ++r) {
-        if (!keys[r] || key_lens[r] < 0 || val_lens[r] < 0 || (val_lens[r] > 0 && !vals[r])) return EGPU_ERR_INVALID;
-        // strings.Split(key, "/") must give exactly two parts (pkg/types/pod.go:40-43)
-        int64_t slashes = 0;
-        for (int64_t i = 0; i < key_lens[r]; ++i) slashes += keys[r][i] == '/';
-        if (slashes != 1) return fail(ctx, EGPU_ERR_PARSE, "error key format", r);
-        std::vector<Entry> entries;
-        Json js(vals[r], val_lens[r]);
-        if (!js.parse_record(entries)) return fail(ctx, EGPU_ERR_PARSE, "error val format", r);
+        if (perr[static_cast<size_t>(r)] == 1) return fail(ctx, EGPU_ERR_PARSE, "error key format", r);
+        if (perr[static_cast<size_t>(r)] == 2) return fail(ctx, EGPU_ERR_PARSE, "error val format", r);
+        std::vector<Entry>& entries = parsed[static_cast<size_t>(r)];
         for (Entry& e : entries) {
             int32_t res = EGPU_RESOURCE_FOREIGN;
             if (e.resource == "elasticgpu.io/gpu-core") res = EGPU_RESOURCE_CORE;

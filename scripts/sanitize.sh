@@ -2,6 +2,7 @@
 # compute-sanitizer over a reduced -m gpu subset (run under gpurun; summaries land in gpurun_out/).
 # memcheck: every kernel family once; racecheck / synccheck: the shared-memory-heavy scans and epilogues.
 set -u
+export EGPU_UNDER_SANITIZER=1  # launches are blocking under the tool: tests skip the start gate (it waits for the host)
 OUT=${1:-gpurun_out}
 mkdir -p "$OUT"
 SUB_A='test_multi_batch_launch_equals_separate_calls and (K3 or 3-) or test_multi_batch_launches_pipelined or test_query_leaves or test_commit_after or test_prefix_commit_cut or test_lookup_scan_with_clustered or test_world1_sharded_multi_batch_and_gate or test_apply_deltas_on_gathered_vectors and G2'
@@ -19,3 +20,4 @@ for tool in memcheck racecheck synccheck; do
 done
 run memcheck devhash python -m pytest tests/test_devhash.py tests/test_restore.py -q -x -m gpu
 run memcheck world2 python -m pytest tests/test_gpu_peer_exchange.py -q -x -m gpu -k "world2_two_processes_one_gpu or world1"
+run racecheck devhash python -m pytest tests/test_devhash.py -q -x -m gpu -k "long_messages or golden_batch"

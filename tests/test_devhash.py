@@ -75,6 +75,29 @@ def test_cuda_device_hash_message_length_sweep(alloc, egpu):
 
 
 @pytest.mark.gpu
+def test_cuda_long_messages_block_count_sweep(alloc, egpu):
+    """The one-CTA-per-message SHA-256 (few long sets): list lengths that put the padded message at
+    30..34 and 63..66 blocks (the 32-block groups of its schedule ring), a 1-block-over-a-group case
+    and the B200 node-scale sizes, full 256-bit digests against hashlib."""
+    import random
+    from elastic_gpu_agent_b200 import devhash
+    rng = random.Random(17)
+    sets = []
+    for n_ids in [256, 257, 300, 330, 340, 341, 342, 343, 350, 680, 700, 701, 702, 703, 704, 710, 1030, 4096, 16384]:
+        sets.append(["%d-%02d" % (rng.randrange(8), j) for j in rng.sample(range(183359), n_ids)])
+    assert sum(len(x) for x in sets) // len(sets) >= 256      # the long-message kernel is the one that runs
+    got, dig = devhash.device_hashes(alloc, sets, want_digest=True)
+    blocks = set()
+    for i, ids in enumerate(sets):
+        msg = ":".join(sorted(ids)).encode()
+        blocks.add((len(msg) + 8) // 64 + 1)
+        ref = hashlib.sha256(msg).hexdigest()
+        assert dig[i] == ref, (i, len(ids))
+        assert got[i] == ref[:8]
+    assert {31, 32, 33} & blocks and {64, 65} & blocks, sorted(blocks)
+
+
+@pytest.mark.gpu
 def test_cuda_many_sets_node_scale(alloc, egpu):
     """A node's worth of candidates: 96 containers x 4096..16384 memory IDs across 8 GPUs."""
     from elastic_gpu_agent_b200 import devhash

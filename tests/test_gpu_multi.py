@@ -3,6 +3,8 @@ the stateless query (egpu_bestfit_query), the start gate, the all-gather form of
 multi-GPU step (egpu_table_apply_deltas_dev + sharding.sharded_step) and the two launch-order
 cases the round-1 review found.  Expected values come from the CPU oracle ("bit-exact" =
 CUDA == builder-defined oracle; the reference has no best-fit path)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -352,12 +354,16 @@ def test_world1_sharded_multi_batch_and_gate(name, fused, alloc, oracle_c, egpu)
     with torch.cuda.stream(st):
         host, tens, tup = _dev_batches(torch, egpu, w["dist"], range(50, 50 + K), rows, D)
     torch.cuda.synchronize()
+    # compute-sanitizer makes kernel launches blocking: a gate kernel would wait for a host that is stuck in its launch
+    gated = not os.environ.get("EGPU_UNDER_SANITIZER")
     for rep in range(2):  # the second pass reuses the same exchange steps: the first must have consumed its flags
-        alloc.gate_dev(st.cuda_stream)
+        if gated:
+            alloc.gate_dev(st.cuda_stream)
         alloc.bestfit_batches_shard_dev(tup, first, st.cuda_stream, inputs_ready=True, apply=fused)
         if not fused:
             alloc.apply_peers_multi_dev(first, [t[4].data_ptr() for t in tens], False, ap.cuda_stream)
-        alloc.gate_open()
+        if gated:
+            alloc.gate_open()
         torch.cuda.synchronize()
         assert alloc.peer_last_timeout == 0
         _check_batches(oracle_c, w, host, tens, rows, D)
