@@ -356,9 +356,10 @@ def main():
     ap.add_argument("--workload", default="cfg3_1m", help="cfg2 | cfg3 | cfg3_1m | cfg4 | cfg3_64mi")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-apply", "nccl"],
-                    help="N > 1: demand vectors pushed to peer memory by the scan kernel, table' written by the same launch "
-                         "(peer, default) or by apply launches on a second stream (peer-apply); or NCCL all-gather + apply_deltas")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-fused", "nccl"],
+                    help="N > 1: demand vectors pushed to peer memory by the scan kernel; table' written by one apply launch per "
+                         "scan launch on a second stream (peer, default: measured fastest) or by the scan launch itself "
+                         "(peer-fused, EGPU_F_APPLY); or NCCL all-gather + apply_deltas")
     ap.add_argument("--force-peer", action="store_true", help="experiment: the sharded step structure even at N = 1 (exchange with self)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds per CPU-baseline leg")
     args = ap.parse_args()
@@ -404,9 +405,9 @@ def main():
     D, R, nb = leg.D, leg.R, leg.nb
     torch.cuda.synchronize()
 
-    use_peer = (world > 1 and args.exchange in ("peer", "peer-apply")) or args.force_peer
+    use_peer = (world > 1 and args.exchange in ("peer", "peer-fused")) or args.force_peer
     use_nccl = world > 1 and args.exchange == "nccl"
-    two_stream = use_peer and args.exchange == "peer-apply"
+    two_stream = use_peer and args.exchange == "peer"
     apply_stream = torch.cuda.Stream() if two_stream else None
     mode = "apply" if two_stream else "fused" if use_peer else "single"
     if use_peer:
