@@ -232,7 +232,8 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     int64_t want = (nvec + per_cta - 1) / per_cta;
     int per_sm = l.ctas_per_sm;
     if (ctx->ctas_per_sm_cap > 0 && ctx->ctas_per_sm_cap < per_sm) per_sm = ctx->ctas_per_sm_cap;
-    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm;
+    // one resident wave; two for a huge batch (the CTA scheduler then evens out the SMs, see launch_multi)
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * ((R >= (16ll << 20) && !contig) ? 2 : 1);
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     // lane-private sums hold 2^19 rows per lane (kAccShift): keep rows/thread below that
@@ -362,7 +363,11 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     if (tiles < 1) tiles = 1;
     int per_sm = l.ctas_per_sm;
     if (ctx->ctas_per_sm_cap > 0 && ctx->ctas_per_sm_cap < per_sm) per_sm = ctx->ctas_per_sm_cap;
-    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * ctx->multi_waves;  // CTAs resident at once (x waves)
+    // CTAs resident at once, x waves.  One wave is best for 1 M-row batches (every extra CTA is an extra
+    // epilogue); for a few huge batches two waves of half-size CTAs let the hardware's CTA scheduler even
+    // out the SMs (64 Mi rows: 129 -> 124 us per batch, same-box A/B with EGPU_MULTI_WAVES)
+    const int waves = ctx->multi_waves > 0 ? ctx->multi_waves : (max_r >= (16ll << 20) ? 2 : 1);
+    const int64_t cap = static_cast<int64_t>(ctx->sm_count) * per_sm * waves;
     int64_t extra = 0;
     if (tiles * K > cap) {  // capped: hand the resident CTAs out evenly, the first `extra` batches get one more
         tiles = cap / K;
@@ -656,6 +661,7 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         if (const char* e = std::getenv("EGPU_CTAS_PER_SM")) ctx->ctas_per_sm_cap = std::atoi(e);
         if (const char* e = std::getenv("EGPU_ROWS_PER_THREAD")) ctx->rows_per_thread = std::atoi(e);
         if (const char* e = std::getenv("EGPU_REPLAY_GENERAL")) ctx->replay_general = std::atoi(e) != 0;
+        if (const char* e = std::getenv("EGPU_REPLAY_VARIANT")) ctx->replay_variant = std::atoi(e);
         if (const char* e = std::getenv("EGPU_THREADS8")) {
             const int v = std::atoi(e);
             ctx->threads8 = (v == 128 || v == 512) ? v : 256;
@@ -663,7 +669,7 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
         if (const char* e = std::getenv("EGPU_LUT_ACC"))
             ctx->lut_acc = std::strcmp(e, "atomic3") == 0 ? 0 : std::strcmp(e, "pair") == 0 ? 2 : 1;
         if (const char* e = std::getenv("EGPU_LONE_FIRST")) ctx->lone_first = std::atoi(e) != 0;
-        if (const char* e = std::getenv("EGPU_MULTI_WAVES")) ctx->multi_waves = std::max(1, std::min(8, std::atoi(e)));
+        if (const char* e = std::getenv("EGPU_MULTI_WAVES")) ctx->multi_waves = std::max(0, std::min(8, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_MULTI_RPT")) ctx->multi_rpt = std::max(4, std::min(4096, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {
             const int g = std::atoi(e);
@@ -1321,7 +1327,15 @@ int egpu_replay(egpu_ctx* ctx, const int32_t* kind, const int32_t* a, const int3
     EGPU_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
     ctx->prev_is_scan = false;
     ctx->lut_dirty = true;
-    if (ctx->D <= 8 && !ctx->replay_general)
+    if (ctx->D <= 32 && E <= kReplaySmemEvents && ctx->replay_variant == 2) {
+        // two warps: decode off the chain, lane = device on it (default wherever it applies)
+        const size_t smem2 = static_cast<size_t>((E + 15) & ~15ll);
+        if (!ctx->replay2_configured) {
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(replay2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemEvents));
+            ctx->replay2_configured = true;
+        }
+        replay2_kernel<<<1, 64, smem2, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out);
+    } else if (ctx->D <= 8 && !ctx->replay_general)
         replay8_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, d_live);
     else
         replay_kernel<<<1, 32, smem, s>>>(ctx->d_state, d_kind, d_a, d_b, E, d_out, d_live);

@@ -91,13 +91,15 @@ struct egpu_ctx {
     Range multi_ranges[3 * kMultiMax];  // scratch of launch_multi
     int lone_first = 0;               // a launch that cannot overlap a predecessor gets the lone-launch grid even on a
                                       // stream declared pipelined (EGPU_LONE_FIRST=0: round 1's sizing, for A/B)
-    int multi_waves = 1;              // multi-batch launches: CTA waves the grid may hold (EGPU_MULTI_WAVES)
+    int multi_waves = 0;              // multi-batch launches: CTA waves the grid may hold (EGPU_MULTI_WAVES; 0 = by batch size)
     int multi_rpt = 8;                // ... and the fewest rows per thread worth a CTA (EGPU_MULTI_RPT)
     int pipe_group = 24;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
     int ctas_per_sm_cap = 0;          // 0 = occupancy limit (EGPU_CTAS_PER_SM overrides)
     int rows_per_thread = 0;          // grid sizing target (EGPU_ROWS_PER_THREAD), 0 = default
     int packed_ctas_per_sm[4] = {0, 0, 0, 0};  // occupancy of the packed-format scan per D bucket, 0 = not asked yet
     int threads8 = 256;               // CTA size of the D <= 8 register scan (EGPU_THREADS8 = 128 | 256 | 512)
+    int replay_variant = 2;           // 2 = two-warp kernel where it applies (EGPU_REPLAY_VARIANT=1: round 1's one-warp kernels)
+    bool replay2_configured = false;
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
     int lut_acc = 1;                  // demand sums of the lookup scan: 1 = two packed unconditional shared-memory
                                       // adds into rotated copies (default), 0 = round 1's three conditional adds

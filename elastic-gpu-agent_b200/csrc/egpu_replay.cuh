@@ -238,4 +238,105 @@ replay8_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, cons
 }
 
 
+// Sequential mode, two warps (D <= 32, E <= kReplaySmemEvents): the serial chain alone on one warp.
+// Warp 1 decodes events 256 at a time into a shared-memory ring - loads, the packed request word, and for a
+// FREE the validity of its target (an earlier ALLOC) and that ALLOC's request word - and writes the previous
+// chunk's results out, coalesced.  Warp 0 walks the ring with lane = device: one broadcast 128-bit read per
+// event, and per ALLOC the dependent path is subtract -> guard test -> select -> CREDUX.MIN -> compare ->
+// select (the chosen lane keeps K - Q, which is its updated table word); a FREE adds the request word back on
+// the lane `live` names.  Every lane keeps `live` redundantly (same address, same value), so a lane always
+// reads its own earlier store and no shuffle or barrier sits between an ALLOC and the FREE that names it.
+constexpr int kReplayChunk = 256;
+struct ReplayRing {
+    uint4 ev[2][kReplayChunk];   // x = request word (ALLOC: its own; FREE: its target's), y = FREE target event or -1, z = kind
+    int32_t res[2][kReplayChunk];
+};
+__global__ void __launch_bounds__(64)
+replay2_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, const int32_t* __restrict__ ev_a,
+               const int32_t* __restrict__ ev_b, long long E, int32_t* __restrict__ out_idx) {
+    // the ring is a static object and `live` the dynamic one: the compiler can see that ring reads never
+    // alias `live` stores and hoists the next events' reads above the current event's stores
+    __shared__ ReplayRing ring;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    signed char* __restrict__ live = reinterpret_cast<signed char*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = st->D;
+    uint32_t K = lane < D ? (pack_table_word(st->free_core[lane], st->free_mem[lane]) | static_cast<uint32_t>(lane)) : kPadWord;
+    const long long n_chunks = (E + kReplayChunk - 1) / kReplayChunk;
+
+    auto decode = [&](long long c) {  // warp 1
+        const long long base = c * kReplayChunk;
+        for (int j = lane; j < kReplayChunk; j += 32) {
+            const long long i = base + j;
+            uint4 e = make_uint4(0u, 0xFFFFFFFFu, 2u, 0u);  // past the end: a no-op kind
+            if (i < E) {
+                const int32_t k = kind[i], a = ev_a[i], b = ev_b[i];
+                e.z = static_cast<uint32_t>(k);
+                if (k == 0) {
+                    e.x = pack_request_word(a, b);
+                } else if (k == 1 && a >= 0 && a < i && kind[a] == 0) {  // FREE of an earlier ALLOC
+                    e.y = static_cast<uint32_t>(a);
+                    e.x = pack_request_word(ev_a[a], ev_b[a]);
+                }
+            }
+            ring.ev[c & 1][j] = e;
+        }
+    };
+    auto drain = [&](long long c) {  // warp 1: results of chunk c to HBM
+        const long long base = c * kReplayChunk;
+        for (int j = lane; j < kReplayChunk; j += 32)
+            if (base + j < E) out_idx[base + j] = ring.res[c & 1][j];
+    };
+    if (warp == 1) decode(0);
+    __syncthreads();
+    for (long long c = 0; c < n_chunks; ++c) {
+        if (warp == 1) {
+            if (c + 1 < n_chunks) decode(c + 1);
+            if (c > 0) drain(c - 1);
+        } else {
+            const long long base = c * kReplayChunk;
+            const int n = (E - base) < kReplayChunk ? static_cast<int>(E - base) : kReplayChunk;
+            const uint4* evs = ring.ev[c & 1];
+            int32_t* res_out = ring.res[c & 1];
+            uint4 nxt = evs[0];
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const uint4 e = nxt;
+                nxt = evs[(j + 1) & (kReplayChunk - 1)];  // one event ahead: its read latency is off the chain
+                // Branch-free: one warp alone pays a pipeline refill for every taken branch, which cost more
+                // than the work it skipped.  Both kinds are computed, the event's kind selects.
+                const bool is_alloc = e.z == 0u;
+                const int32_t t = static_cast<int32_t>(e.y);            // FREE target (an earlier ALLOC) or -1
+                const int32_t tdev_raw = live[t < 0 ? 0 : t];           // read before this event's stores
+                // ALLOC: K - Q is never 0xFFFFFFFF (Q's low five bits are zero, K's hold a device < 32), so no
+                // lane matches "none"; a FREE / no-op event carries INF on every lane
+                const uint32_t w = K - e.x;
+                const uint32_t key = (is_alloc && (~w & kGuards) == 0u) ? w : 0xFFFFFFFFu;
+                const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+                const int32_t a_res = best == 0xFFFFFFFFu ? -1 : static_cast<int32_t>(best & 31u);
+                const int32_t tdev = t >= 0 ? tdev_raw : -1;
+                const int32_t res = is_alloc ? a_res : tdev;
+                const uint32_t k_alloc = (w == best) ? w : K;
+                const uint32_t k_free = (lane == tdev) ? K + e.x : K;
+                K = is_alloc ? k_alloc : k_free;
+                live[base + j] = static_cast<signed char>(is_alloc ? a_res : -1);
+                if (t >= 0) live[t] = -1;
+                res_out[j] = res;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 1 && n_chunks > 0) drain(n_chunks - 1);
+    __shared__ int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
+    if (warp == 0 && lane < D) {
+        const int32_t fc = static_cast<int32_t>((K >> 24) & 0x7Fu), fm = static_cast<int32_t>((K >> 5) & 0x3FFFFu);
+        st->free_core[lane] = fc;
+        st->free_mem[lane] = fm;
+        sFc[lane] = fc;
+        sFm[lane] = fm;
+    }
+    __syncthreads();
+    resort_table_cta(st, D, sFc, sFm, sPosDev, tid);
+}
+
 }  // namespace egpu

@@ -107,7 +107,7 @@ def timed_eager(fn, reps=31):
 
 
 if ONLY_MULTI:
-    f = multi(min(K, 64))
+    f = multi(min(K, 64, nb))
     for _ in range(3):
         f(sh)
     torch.cuda.synchronize()
@@ -118,10 +118,10 @@ peak = 6583.5
 out = {"workload": name, "K": K, "D": D, "R": R, "env": {k: v for k, v in os.environ.items() if k.startswith("EGPU_")}}
 r = timed(graph_of(singles))
 out["single_launches"] = r
-for chunk in sorted({min(K, 64), min(K, 10), min(K, 32)}, reverse=True):
+for chunk in sorted({min(K, 64, nb), min(K, 10, nb), min(K, 32, nb), 1}, reverse=True):
     r = timed(graph_of(multi(chunk)))
     out[f"multi_chunk{chunk}"] = r
-out["multi_eager"] = timed_eager(multi(min(K, 64)))
+out["multi_eager"] = timed_eager(multi(min(K, 64, nb)))
 for k, v in out.items():
     if isinstance(v, dict) and "us_per_batch_median" in v:
         v["frac_of_hbm_peak"] = (12 * R + 32 * D) / (v["us_per_batch_median"] * 1e-6) / 1e9 / peak
