@@ -115,19 +115,9 @@ int configure_launch(egpu_ctx* ctx, SnapLaunch& l, int D, bool grid_variant, boo
     const int bucket = D <= 8 ? 0 : D <= 16 ? 1 : D <= 32 ? 2 : 3;
     int per_sm = 0;
     if (lut_variant) {
-        // demand sums: ACC 1 = two unconditional packed adds into 8 rotated copies per warp
-        // (default), ACC 0 = round 1's three conditional adds (EGPU_LUT_ACC=atomic3, for A/B)
         l.threads = 256;
-        if (ctx->lut_acc == 0) {
-            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 0> : bestfit_lut_kernel<256, false, 0>;
-            l.smem = sizeof(LutSmem<256, 0>);
-        } else if (ctx->lut_acc == 2) {
-            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 2> : bestfit_lut_kernel<256, false, 2>;
-            l.smem = sizeof(LutSmem<256, 2>);
-        } else {
-            l.lut_fn = contig ? bestfit_lut_kernel<256, true, 1> : bestfit_lut_kernel<256, false, 1>;
-            l.smem = sizeof(LutSmem<256, 1>);
-        }
+        l.lut_fn = contig ? bestfit_lut_kernel<256, true> : bestfit_lut_kernel<256, false>;
+        l.smem = sizeof(LutSmem<256>);
         EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
         EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
     } else {
@@ -220,10 +210,9 @@ int launch_snapshot(egpu_ctx* ctx, const int32_t* d_rc, const int32_t* d_rm, int
     // B200 at R = 1M.  The zero-copy path passes its own hint (see egpu_bestfit_batch).
     const int64_t nvec = R >> 2;
     int rpt = 8;
-    // (a launch that could not be pipelined has nothing to overlap with: it keeps the lone-launch
-    // grid even on a stream the caller declared pipelined - e.g. the first launch of a graph)
-    if ((user_flags & EGPU_F_INPUTS_READY) && (pipelined || ctx->lone_first == 0))
-        rpt = (lut_variant || ctx->D <= 16) ? 48 : 8;  // measured, scripts/tune_*.sh
+    // (measured and dropped: giving the launches of a pipelined stream that could not themselves be
+    // pipelined - the first of a graph - the lone-launch grid: 2.80 against 2.68 us per step)
+    if (user_flags & EGPU_F_INPUTS_READY) rpt = (lut_variant || ctx->D <= 16) ? 48 : 8;  // measured, scripts/tune_*.sh
     else if (lut_variant) rpt = 32;  // the lookup scan has a 13 KB per-CTA table tile to amortise
     if (rpt_hint > 0) rpt = rpt_hint;
     if (ctx->rows_per_thread > 0) rpt = ctx->rows_per_thread;
@@ -292,10 +281,9 @@ int launch_multi(egpu_ctx* ctx, const egpu_batch* bs, int K, int user_flags, cud
     if (l.ctas_per_sm == 0) {
         int per_sm = 0;
         if (lut_variant) {
-            l.lut_fn = ctx->lut_acc == 0 ? bestfit_lut_multi_kernel<256, 0>
-                       : ctx->lut_acc == 2 ? bestfit_lut_multi_kernel<256, 2> : bestfit_lut_multi_kernel<256, 1>;
+            l.lut_fn = bestfit_lut_multi_kernel<256>;
             l.threads = 256;
-            l.smem = ctx->lut_acc == 0 ? sizeof(LutSmem<256, 0>) : ctx->lut_acc == 2 ? sizeof(LutSmem<256, 2>) : sizeof(LutSmem<256, 1>);
+            l.smem = sizeof(LutSmem<256>);
             EGPU_CUDA(ctx, cudaFuncSetAttribute(l.lut_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(l.smem)));
             EGPU_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l.lut_fn, l.threads, l.smem));
         } else {
@@ -666,9 +654,6 @@ int egpu_ctx_create(int cuda_device, egpu_ctx** out) {
             const int v = std::atoi(e);
             ctx->threads8 = (v == 128 || v == 512) ? v : 256;
         }
-        if (const char* e = std::getenv("EGPU_LUT_ACC"))
-            ctx->lut_acc = std::strcmp(e, "atomic3") == 0 ? 0 : std::strcmp(e, "pair") == 0 ? 2 : 1;
-        if (const char* e = std::getenv("EGPU_LONE_FIRST")) ctx->lone_first = std::atoi(e) != 0;
         if (const char* e = std::getenv("EGPU_MULTI_WAVES")) ctx->multi_waves = std::max(0, std::min(8, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_MULTI_RPT")) ctx->multi_rpt = std::max(4, std::min(4096, std::atoi(e)));
         if (const char* e = std::getenv("EGPU_PIPE_GROUP")) {

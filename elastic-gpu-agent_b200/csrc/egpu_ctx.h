@@ -89,8 +89,6 @@ struct egpu_ctx {
     std::vector<Range> inflight;      // output ranges of those launches, sorted by address, pairwise disjoint
     std::vector<Range> range_tmp;
     Range multi_ranges[3 * kMultiMax];  // scratch of launch_multi
-    int lone_first = 0;               // a launch that cannot overlap a predecessor gets the lone-launch grid even on a
-                                      // stream declared pipelined (EGPU_LONE_FIRST=0: round 1's sizing, for A/B)
     int multi_waves = 0;              // multi-batch launches: CTA waves the grid may hold (EGPU_MULTI_WAVES; 0 = by batch size)
     int multi_rpt = 8;                // ... and the fewest rows per thread worth a CTA (EGPU_MULTI_RPT)
     int pipe_group = 24;              // launches per group (EGPU_PIPE_GROUP, <= kPipeGroupMax)
@@ -101,9 +99,6 @@ struct egpu_ctx {
     int replay_variant = 2;           // 2 = two-warp kernel where it applies (EGPU_REPLAY_VARIANT=1: round 1's one-warp kernels)
     bool replay2_configured = false;
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
-    int lut_acc = 1;                  // demand sums of the lookup scan: 1 = two packed unconditional shared-memory
-                                      // adds into rotated copies (default), 0 = round 1's three conditional adds
-                                      // (EGPU_LUT_ACC=atomic3, kept for A/B)
     // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
     void* arena = nullptr;
     size_t arena_cap = 0;

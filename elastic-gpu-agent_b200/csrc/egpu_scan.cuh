@@ -713,45 +713,33 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
 }
 
 // Demand sums of the lookup scan.  64-bit shared-memory adds compile to CAS loops on sm_100a
-// (ATOMS.CAST.SPIN.64), lane-private 64-bit sums cost 16.6 KB per warp; what is used instead
-// is native 32-bit ATOMS.ADD on small per-warp tables, folded into 64-bit sums before a word
-// could overflow.
-//   ACC = 0  one table per warp, three words per device (core, mem & 0xffff, mem >> 16 - the
-//            last only when non-zero), infeasible rows issue nothing (two branch regions per
-//            request); fold every 128 trips.  Round 1's form, kept for A/B (EGPU_LUT_ACC=atomic3).
-//   ACC = 1  two UNCONDITIONAL adds per request - word 0 = core | (mem >> 16) << 20, word 1 =
-//            mem & 0xffff - into one of 8 copies of the table per warp (copy = lane / 4; the
-//            copies are 140 words apart, i.e. rotated by 12 banks, so the hot devices of a batch
-//            spread over the banks), infeasible rows into a per-lane dummy word: no branches,
-//            no shared hot spot.  A copy receives 4 lanes x 8 rows per trip, so word 0's 12-bit
-//            mem >> 16 field (<= 3 per add) lasts 42 trips: fold every 32.
-//   ACC = 2  no atomics: 64-bit sums (core << 38 | mem, as the register scan keeps them) in columns
-//            owned by lane pairs; the two half-warps take turns (two phases per trip, __syncwarp
-//            between them).  A half-warp read or write of a column set is ONE conflict-free
-//            wavefront, so a decision costs 4 shared-memory wavefronts per warp instead of the
-//            ~7.7 the two adds of ACC 1 take with their bank conflicts - the lookup scan is bound by
-//            the shared-memory pipe (ncu: l1tex data pipe 79 % busy), not by issue slots.  8.3 KB
-//            per warp; no folding needed below 2^19 rows per lane.
-constexpr int kLutFlushTrips3 = 128;  // ACC 0: x 8 rows per thread per trip x 32 lanes = 32 K rows per warp
-constexpr int kLutFlushTrips2 = 32;   // ACC 1
+// (ATOMS.CAST.SPIN.64) and lane-private 64-bit sums cost 16.6 KB per warp; what is used instead is
+// native 32-bit ATOMS.ADD: two UNCONDITIONAL adds per request - word 0 = core | (mem >> 16) << 20,
+// word 1 = mem & 0xffff - into one of 8 copies of a small table per warp (copy = lane / 4; the
+// copies are 140 words apart, i.e. rotated by 12 banks, so the hot devices of a batch spread over
+// the banks), infeasible rows into a per-lane dummy word: no branches, no shared hot spot.  A copy
+// receives 4 lanes x 8 rows per trip, so word 0's 12-bit mem >> 16 field (<= 3 per add) lasts 42
+// trips: the words are folded into 64-bit register sums every 32.
+// (Measured and dropped, DESIGN.md 7.2: round 1's three conditional adds into one table per warp;
+// 64-bit sums in columns owned by lane pairs with the half-warps taking turns - fewer shared-memory
+// wavefronts, 7.95 M against 10.3 M per 20 M decisions, but 8.3 KB per warp halves the occupancy.)
+constexpr int kLutFlushTrips = 32;
 constexpr int kLutCopies = 8;
 constexpr int kLutPlane = kMaxD + 4;                 // 64 devices + one dummy word per lane of the copy
 constexpr int kLutCopyStride = 2 * kLutPlane + 4;    // 140 words = 12 banks
-template <int THREADS, int ACC>
+template <int THREADS>
 struct LutSmem {
     DevLut lut;
     unsigned long long sWarpAcc[THREADS / 32][2 * kMaxD];
     int32_t sFc[kMaxD], sFm[kMaxD], sPosDev[kMaxD];
     int sLast;
-    // ACC 0 / 1: 32-bit words for ATOMS.ADD; ACC 2: 64-bit sums, one column per lane PAIR (lane, lane ^ 16),
-    // [device + 1][lane & 15] - bank = 2 * (lane & 15): conflict-free, a half-warp access is one wavefront
-    alignas(16) uint32_t hist32[THREADS / 32][ACC == 0 ? 3 * kMaxD : ACC == 1 ? kLutCopies * kLutCopyStride : (kMaxD + 1) * 16 * 2];
+    alignas(16) uint32_t hist32[THREADS / 32][kLutCopies * kLutCopyStride];
 };
 
 // The lookup scan of one batch by one CTA (tile `tile_i` of `n_tiles`, as sorted_scan_rows).
 // Leaves the warp sums in sm.sWarpAcc; the caller synchronises and runs epilogue_publish.
-template <int THREADS, bool CONTIG, int ACC>
-__device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState* __restrict__ st,
+template <int THREADS, bool CONTIG>
+__device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS>& sm, DevState* __restrict__ st,
                                              const int32_t* __restrict__ req_core, const int32_t* __restrict__ req_mem,
                                              long long R, int32_t* __restrict__ out_idx, const DevLut* __restrict__ glut,
                                              int tile_i, int n_tiles) {
@@ -799,7 +787,7 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
     __syncthreads();
     const DevLut& L = sm.lut;
     uint32_t* const hw = &sm.hist32[warp][0];
-    uint32_t* const hcopy = hw + (ACC == 1 ? (lane >> 2) * kLutCopyStride : 0);
+    uint32_t* const hcopy = hw + (lane >> 2) * kLutCopyStride;
     const uint32_t dummy_col = static_cast<uint32_t>(kMaxD) + (static_cast<uint32_t>(lane) & 3u);
 
     // device (0..63) or 0xFF for one request: two dependent shared-memory reads, no branch
@@ -815,50 +803,32 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
     };
     // fold this warp's 32-bit words into the 64-bit sums and clear them
     auto flush32 = [&]() {
-        if constexpr (ACC == 2) return;
         __syncwarp();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int d = lane + 32 * half;
-            if constexpr (ACC == 0) {
-                const uint32_t hc = hw[d], hl = hw[kMaxD + d], hh = hw[2 * kMaxD + d];
-                hw[d] = 0u;
-                hw[kMaxD + d] = 0u;
-                hw[2 * kMaxD + d] = 0u;
-                acc_c[half] += hc;
-                acc_m[half] += static_cast<unsigned long long>(hl) + (static_cast<unsigned long long>(hh) << 16);
-            } else {
-                uint32_t cs = 0, mh = 0, ml = 0;
+            uint32_t cs = 0, mh = 0, ml = 0;
 #pragma unroll
-                for (int j = 0; j < kLutCopies; ++j) {  // bank = (12 j + lane) mod 32: conflict-free
-                    uint32_t* h = hw + j * kLutCopyStride;
-                    const uint32_t w0 = h[d], w1 = h[kLutPlane + d];
-                    h[d] = 0u;
-                    h[kLutPlane + d] = 0u;
-                    cs += w0 & 0xFFFFFu;
-                    mh += w0 >> 20;
-                    ml += w1;
-                }
-                acc_c[half] += cs;
-                acc_m[half] += static_cast<unsigned long long>(ml) + (static_cast<unsigned long long>(mh) << 16);
+            for (int j = 0; j < kLutCopies; ++j) {  // bank = (12 j + lane) mod 32: conflict-free
+                uint32_t* h = hw + j * kLutCopyStride;
+                const uint32_t w0 = h[d], w1 = h[kLutPlane + d];
+                h[d] = 0u;
+                h[kLutPlane + d] = 0u;
+                cs += w0 & 0xFFFFFu;
+                mh += w0 >> 20;
+                ml += w1;
             }
+            acc_c[half] += cs;
+            acc_m[half] += static_cast<unsigned long long>(ml) + (static_cast<unsigned long long>(mh) << 16);
         }
         __syncwarp();
     };
     auto add1 = [&](uint32_t dev, int32_t core, int32_t mem) {
-        if constexpr (ACC == 0) {
-            if (dev < static_cast<uint32_t>(kMaxD)) {  // feasible rows are inside the domain: core <= 100, mem < 2^18
-                atomicAdd(&hw[dev], static_cast<uint32_t>(core));
-                atomicAdd(&hw[kMaxD + dev], static_cast<uint32_t>(mem) & 0xffffu);
-                if (mem >> 16) atomicAdd(&hw[2 * kMaxD + dev], static_cast<uint32_t>(mem) >> 16);
-            }
-        } else {
-            // infeasible rows (0xFF) go to this lane's dummy word, whose content is never read
-            // (their core / mem may be anything: nothing carries from one word into another)
-            const uint32_t col = min(dev, dummy_col);
-            atomicAdd(&hcopy[col], static_cast<uint32_t>(core) | ((static_cast<uint32_t>(mem) >> 16) << 20));
-            atomicAdd(&hcopy[kLutPlane + col], static_cast<uint32_t>(mem) & 0xffffu);
-        }
+        // infeasible rows (0xFF) go to this lane's dummy word, whose content is never read
+        // (their core / mem may be anything: nothing carries from one word into another)
+        const uint32_t col = min(dev, dummy_col);
+        atomicAdd(&hcopy[col], static_cast<uint32_t>(core) | ((static_cast<uint32_t>(mem) >> 16) << 20));
+        atomicAdd(&hcopy[kLutPlane + col], static_cast<uint32_t>(mem) & 0xffffu);
     };
     auto decide = [&](int32_t core, int32_t mem) -> int32_t {
         const uint32_t dev = lookup(core, mem);
@@ -877,31 +847,12 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
         add1(d.z, c.z, m.z);
         add1(d.w, c.w, m.w);
     };
-    // ACC 2: the eight requests of a trip, one half-warp at a time
-    unsigned long long* const h64 = reinterpret_cast<unsigned long long*>(hw) + (lane & 15);
-    auto add8_pair = [&](const uint4& d0, const int4& c0, const int4& m0, const uint4& d1, const int4& c1, const int4& m1) {
-        auto one = [&](uint32_t dev, int32_t core, int32_t mem) {
-            // row 0 absorbs infeasible rows (0xFF -> 0); its content is never read
-            const uint32_t row = (dev + 1u) & 0x7Fu;
-            h64[row * 16u] += (static_cast<unsigned long long>(static_cast<uint32_t>(core)) << kAccShift) |
-                              static_cast<unsigned long long>(static_cast<uint32_t>(mem));
-        };
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            if ((lane >> 4) == p) {
-                one(d0.x, c0.x, m0.x); one(d0.y, c0.y, m0.y); one(d0.z, c0.z, m0.z); one(d0.w, c0.w, m0.w);
-                one(d1.x, c1.x, m1.x); one(d1.y, c1.y, m1.y); one(d1.z, c1.z, m1.z); one(d1.w, c1.w, m1.w);
-            }
-            __syncwarp();
-        }
-    };
     auto as_idx4 = [](const uint4& d) -> int4 {
         return make_int4(static_cast<int8_t>(d.x), static_cast<int8_t>(d.y), static_cast<int8_t>(d.z), static_cast<int8_t>(d.w));
     };
-    constexpr int kFlushTrips = ACC == 0 ? kLutFlushTrips3 : kLutFlushTrips2;
     int trips = 0;
     while (__any_sync(0xffffffffu, has0)) {  // warp-uniform trip count: flush32() synchronises the warp
-        if (++trips == kFlushTrips) {
+        if (++trips == kLutFlushTrips) {
             flush32();
             trips = 0;
         }
@@ -922,12 +873,8 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
         const uint4 d1 = lookup4(c1, m1);
         if (has0) st_stream_v4(vo + v, as_idx4(d0));
         if (has1) st_stream_v4(vo + (v + stride), as_idx4(d1));
-        if constexpr (ACC == 2) {
-            add8_pair(d0, c0, m0, d1, c1, m1);
-        } else {
-            add4(d0, c0, m0);
-            add4(d1, c1, m1);
-        }
+        add4(d0, c0, m0);
+        add4(d1, c1, m1);
         v = vn;
         has0 = nhas0;
         has1 = nhas1;
@@ -939,32 +886,9 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
         const int32_t c = mine ? req_core[r] : -1, m = mine ? req_mem[r] : -1;
         const uint32_t dev = lookup(c, m);
         if (mine) out_idx[r] = static_cast<int32_t>(static_cast<int8_t>(dev));
-        if constexpr (ACC == 2) {
-            const uint4 none = make_uint4(0xFFu, 0xFFu, 0xFFu, 0xFFu);
-            const int4 z = make_int4(0, 0, 0, 0);
-            add8_pair(make_uint4(dev, 0xFFu, 0xFFu, 0xFFu), make_int4(c, 0, 0, 0), make_int4(m, 0, 0, 0), none, z, z);
-        } else {
-            add1(dev, c, m);
-        }
+        add1(dev, c, m);
     }
     flush32();
-    if constexpr (ACC == 2) {  // lane L adds up the 16 columns of devices L and L + 32 (rotated start: conflict-free)
-        __syncwarp();
-        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hw);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int d = lane + 32 * half;
-            unsigned long long sc = 0, smm = 0;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const unsigned long long hv = h[(d + 1) * 16 + ((k + lane) & 15)];
-                sc += hv >> kAccShift;
-                smm += hv & ((1ull << kAccShift) - 1ull);
-            }
-            acc_c[half] = sc;
-            acc_m[half] = smm;
-        }
-    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         sm.sWarpAcc[warp][lane + 32 * half] = acc_c[half];
@@ -973,19 +897,19 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS, ACC>& sm, DevState
     return D;
 }
 
-template <int THREADS, bool CONTIG = false, int ACC = 1>
+template <int THREADS, bool CONTIG = false>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_core,
                    const int32_t* __restrict__ req_mem, long long R, int32_t* __restrict__ out_idx,
                    long long* __restrict__ delta_out, int32_t* __restrict__ table_out, int flags, unsigned long long slot_step,
                    const DevLut* __restrict__ glut, unsigned long long* __restrict__ tile_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& sm = *reinterpret_cast<LutSmem<THREADS, ACC>*>(smem_raw);
+    auto& sm = *reinterpret_cast<LutSmem<THREADS>*>(smem_raw);
     const bool late = (flags & kFlagLateWait) != 0;
     const bool boundary = (flags & kFlagBoundary) != 0;
     if (!late) pdl_wait();
     if ((flags & kFlagEarlyTrigger) && !boundary) pdl_trigger();
-    const int D = lut_scan_rows<THREADS, CONTIG, ACC>(sm, st, req_core, req_mem, R, out_idx, glut, static_cast<int>(blockIdx.x),
+    const int D = lut_scan_rows<THREADS, CONTIG>(sm, st, req_core, req_mem, R, out_idx, glut, static_cast<int>(blockIdx.x),
                                                       static_cast<int>(gridDim.x));
     if (boundary) {
         pdl_wait();
@@ -998,12 +922,12 @@ bestfit_lut_kernel(DevState* __restrict__ st, const int32_t* __restrict__ req_co
 }
 
 // Multi-batch form of the lookup scan (see bestfit_sorted_multi_kernel).
-template <int THREADS, int ACC>
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ MultiArgs args, int tiles_extra, int flags,
                          unsigned int slot_base, unsigned long long push_base, const DevLut* __restrict__ glut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    auto& sm = *reinterpret_cast<LutSmem<THREADS, ACC>*>(smem_raw);
+    auto& sm = *reinterpret_cast<LutSmem<THREADS>*>(smem_raw);
     const bool late = (flags & kFlagLateWait) != 0;
     const bool boundary = (flags & kFlagBoundary) != 0;
     if (!late) pdl_wait();
@@ -1011,7 +935,7 @@ bestfit_lut_multi_kernel(DevState* __restrict__ st, const __grid_constant__ Mult
     int batch, tile_i, tiles;
     multi_cta_to_tile(tiles_extra, batch, tile_i, tiles);
     const BatchDesc b = args.b[batch];
-    const int D = lut_scan_rows<THREADS, false, ACC>(sm, st, b.rc, b.rm, b.R, b.idx, glut, tile_i, tiles);
+    const int D = lut_scan_rows<THREADS, false>(sm, st, b.rc, b.rm, b.R, b.idx, glut, tile_i, tiles);
     if (boundary) {
         pdl_wait();
         pdl_trigger();

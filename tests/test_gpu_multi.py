@@ -130,13 +130,11 @@ def test_lookup_scan_with_clustered_memory_values(alloc, oracle_c, egpu):
         assert np.array_equal(idx, o_idx) and np.array_equal(dc, o_dc) and np.array_equal(dm, o_dm)
 
 
-@pytest.mark.parametrize("acc", ["atomic2", "atomic3", "pair"])
-def test_lookup_scan_sums_survive_many_trips(acc, oracle_c, egpu, monkeypatch):
+def test_lookup_scan_sums_survive_many_trips(oracle_c, egpu, monkeypatch):
     """Every request lands on one device with the largest addends: the 32-bit shared-memory words
     of the lookup scan must be folded before any field overflows (4 M rows on 4 CTAs: 4096 rows
     per thread, 512 trips)."""
     monkeypatch.setenv("EGPU_ROWS_PER_THREAD", "4096")
-    monkeypatch.setenv("EGPU_LUT_ACC", acc)
     alloc = egpu.BestFitAllocator(0)
     D = 64
     fc = np.full(D, 100, dtype=np.int32)
