@@ -244,8 +244,10 @@ replay8_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, cons
 // chunk's results out, coalesced.  Warp 0 walks the ring with lane = device: one broadcast 128-bit read per
 // event, and per ALLOC the dependent path is subtract -> guard test -> select -> CREDUX.MIN -> compare ->
 // select (the chosen lane keeps K - Q, which is its updated table word); a FREE adds the request word back on
-// the lane `live` names.  Every lane keeps `live` redundantly (same address, same value), so a lane always
-// reads its own earlier store and no shuffle or barrier sits between an ALLOC and the FREE that names it.
+// the lane `live` names.  `live` is lane 0's alone (program order is its consistency: racecheck-clean); the
+// device a FREE releases reaches the other lanes through one shuffle.  (All lanes keeping `live` redundantly -
+// same address, same value - saved that shuffle, 40 against 48 ns per event, but is a formal shared-memory race
+// that racecheck reports; warp barriers around a single writer: 80 ns; `if (lane == 0)` as a branch: 87 ns.)
 constexpr int kReplayChunk = 256;
 struct ReplayRing {
     uint4 ev[2][kReplayChunk];   // x = request word (ALLOC: its own; FREE: its target's), y = FREE target event or -1, z = kind
@@ -258,7 +260,7 @@ replay2_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, cons
     // alias `live` stores and hoists the next events' reads above the current event's stores
     __shared__ ReplayRing ring;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    signed char* __restrict__ live = reinterpret_cast<signed char*>(smem_raw);
+    const uint32_t live_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));  // `live`: int8 per event
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = st->D;
     uint32_t K = lane < D ? (pack_table_word(st->free_core[lane], st->free_mem[lane]) | static_cast<uint32_t>(lane)) : kPadWord;
@@ -307,7 +309,14 @@ replay2_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, cons
                 // than the work it skipped.  Both kinds are computed, the event's kind selects.
                 const bool is_alloc = e.z == 0u;
                 const int32_t t = static_cast<int32_t>(e.y);            // FREE target (an earlier ALLOC) or -1
-                const int32_t tdev_raw = live[t < 0 ? 0 : t];           // read before this event's stores
+                // `live` belongs to lane 0 alone (reads and writes in its program order: nothing to race with);
+                // the device a FREE releases reaches the other lanes through one shuffle
+                // (predicated instructions, not branches: a divergent region per event costs more than the event)
+                const uint32_t live_t = live_base + static_cast<uint32_t>(t < 0 ? 0 : t);
+                int32_t tdev0;
+                asm volatile("{ .reg .pred p; setp.eq.s32 p, %1, 0; mov.s32 %0, -1; @p ld.shared.s8 %0, [%2]; }"
+                             : "=r"(tdev0) : "r"(lane), "r"(live_t) : "memory");  // read before this event's stores
+                const int32_t tdev_raw = __shfl_sync(0xffffffffu, tdev0, 0);
                 // ALLOC: K - Q is never 0xFFFFFFFF (Q's low five bits are zero, K's hold a device < 32), so no
                 // lane matches "none"; a FREE / no-op event carries INF on every lane
                 const uint32_t w = K - e.x;
@@ -319,8 +328,13 @@ replay2_kernel(DevState* __restrict__ st, const int32_t* __restrict__ kind, cons
                 const uint32_t k_alloc = (w == best) ? w : K;
                 const uint32_t k_free = (lane == tdev) ? K + e.x : K;
                 K = is_alloc ? k_alloc : k_free;
-                live[base + j] = static_cast<signed char>(is_alloc ? a_res : -1);
-                if (t >= 0) live[t] = -1;
+                {
+                    const int32_t mine = is_alloc ? a_res : -1;
+                    asm volatile("{ .reg .pred p, q; setp.eq.s32 p, %0, 0; setp.ge.and.s32 q, %4, 0, p;\n\t"
+                                 "@p st.shared.u8 [%1], %2; @q st.shared.u8 [%3], %5; }"
+                                 ::"r"(lane), "r"(live_base + static_cast<uint32_t>(base + j)), "r"(mine), "r"(live_t), "r"(t), "r"(-1)
+                                 : "memory");
+                }
                 res_out[j] = res;
             }
         }
