@@ -438,9 +438,11 @@ def main():
         """the n-step region of leg lg on stream s (+ apply stream aps when sharded)"""
         if use_nccl:
             from elastic_gpu_agent_b200 import sharding
+            if not hasattr(lg, "gathered"):
+                lg.gathered = torch.zeros(world * 2 * lg.D, dtype=torch.int64, device=dev)
             for k in range(n):
                 c, m, idx, dl, to = lg.ring[k % lg.nb]
-                sharding.sharded_step(alloc, c.data_ptr(), m.data_ptr(), lg.R, idx.data_ptr(), dl, gathered, to, world, s.cuda_stream)
+                sharding.sharded_step(alloc, c.data_ptr(), m.data_ptr(), lg.R, idx.data_ptr(), dl, lg.gathered, to, world, s.cuda_stream)
             return 2 * n
         return lg.issue(n, s, mode, aps, rec, lambda st, ev: st.wait_event(ev))
 
