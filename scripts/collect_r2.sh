@@ -9,8 +9,8 @@ mkdir -p $O
 (timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err); echo "bench rc=$?" >> $O/r2_gputests.txt
 (timeout 200 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/r2_bench_ref.json 2>> $O/r2_bench_n1.err)
 # launch list of the same command (cold, serialised: shares, not absolutes)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv \
-    python bench.py --gpus 1 --steps 20 --warmup 5 --no-sweep > $O/r2_bench_under_ncu.log 2>&1
+EGPU_BENCH_NO_GATE=1 EGPU_BENCH_REPLAYS=5 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+    --log-file $O/r2_launches.csv python bench.py --gpus 1 --steps 20 --warmup 5 --no-sweep > $O/r2_bench_under_ncu.log 2>&1
 # full captures: the multi-batch launches of the headline (8 devices), of cfg4 (64 devices) and one 64 Mi-row launch
 for spec in "cfg3_1m 20 sorted_multi" "cfg4 20 lut_multi" "cfg3_64mi 2 sorted_64mi"; do
   set -- $spec
