@@ -73,8 +73,14 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
     std::vector<int64_t> count(static_cast<size_t>(D), 0);
     for (int64_t i = 0; i < n_available; ++i) count[gpu_of[i]] += 1;
 
-    // 2. must-include IDs pin the GPU
-    int32_t pinned = -1;
+    // Whole-card requests (gpu-core only): more than 100 core units means allocation_size / 100 whole GPUs,
+    // the reference's len/100 (pkg/plugins/gpushare.go:62-69); the size must then be a multiple of 100.
+    const bool whole_cards = resource == EGPU_RESOURCE_CORE && allocation_size > EGPU_CORE_MAX;
+    if (whole_cards && allocation_size % EGPU_CORE_MAX != 0) return EGPU_ERR_UNSAT;
+    const int32_t n_gpus = whole_cards ? allocation_size / EGPU_CORE_MAX : 1;
+
+    // 2. must-include IDs pin the GPU (whole-card requests: up to n_gpus GPUs)
+    std::vector<int32_t> pinned;
     std::unordered_map<std::string, int32_t> pos_of;
     if (n_must > 0) {
         pos_of.reserve(static_cast<size_t>(n_available) * 2);
@@ -85,36 +91,45 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
             const int rc = egpu_device_id_parse(must_include_ids[k], &g, &u);
             if (rc != EGPU_OK) return rc;
             if (pos_of.find(must_include_ids[k]) == pos_of.end()) return EGPU_ERR_UNSAT;  // kubelet promises must ⊆ available
-            if (pinned >= 0 && g != pinned) return EGPU_ERR_UNSAT;                        // v1: one GPU per container
-            pinned = g;
+            if (std::find(pinned.begin(), pinned.end(), g) == pinned.end()) pinned.push_back(g);
+            if (static_cast<int32_t>(pinned.size()) > n_gpus) return EGPU_ERR_UNSAT;      // spans more GPUs than the request takes
         }
     }
 
-    // 3. the choice: CUDA best-fit over the availability table
+    // 3. the choice: CUDA best-fit over the availability table.  One GPU per pick; a whole-card request
+    //    makes n_gpus picks of a full card each, every pick against the table without the cards already
+    //    taken (the sequential rule of the spec), pinned GPUs first.
     const int64_t cap_units = resource == EGPU_RESOURCE_CORE ? EGPU_CORE_MAX : EGPU_MEM_MAX;
     std::vector<int32_t> free_core(static_cast<size_t>(D)), free_mem(static_cast<size_t>(D));
-    for (int32_t d = 0; d < D; ++d) {
-        const int32_t c = static_cast<int32_t>(std::min<int64_t>(count[d], cap_units));
-        const bool usable = pinned < 0 || d == pinned;
-        free_core[d] = resource == EGPU_RESOURCE_CORE ? (usable ? c : 0) : (usable ? EGPU_CORE_MAX : 0);
-        free_mem[d] = resource == EGPU_RESOURCE_MEM ? (usable ? c : 0) : (usable ? EGPU_MEM_MAX : 0);
+    std::vector<int32_t> chosen;
+    for (int32_t pick = 0; pick < n_gpus; ++pick) {
+        const int32_t pin = pick < static_cast<int32_t>(pinned.size()) ? pinned[static_cast<size_t>(pick)] : -1;
+        for (int32_t d = 0; d < D; ++d) {
+            const int32_t c = static_cast<int32_t>(std::min<int64_t>(count[d], cap_units));
+            const bool taken_card = std::find(chosen.begin(), chosen.end(), d) != chosen.end();
+            // single-GPU requests: only the pinned GPU is usable; whole cards: this pick's pin, and never a later pick's pin
+            const bool later_pin = pin < 0 && std::find(pinned.begin(), pinned.end(), d) != pinned.end();
+            const bool usable = !taken_card && !later_pin && (pin < 0 || d == pin);
+            free_core[d] = resource == EGPU_RESOURCE_CORE ? (usable ? c : 0) : (usable ? EGPU_CORE_MAX : 0);
+            free_mem[d] = resource == EGPU_RESOURCE_MEM ? (usable ? c : 0) : (usable ? EGPU_MEM_MAX : 0);
+        }
+        // a request for 0 units of the constrained resource still needs 1 unit of the other
+        // dimension on unusable GPUs to be excluded: unusable rows are (0, 0), request >= (0, 0)
+        // would fit them, so ask for one unit of the unconstrained dimension
+        int32_t req_core = resource == EGPU_RESOURCE_CORE ? (whole_cards ? EGPU_CORE_MAX : allocation_size) : 1;
+        int32_t req_mem = resource == EGPU_RESOURCE_MEM ? allocation_size : 1;
+        // stateless query against this request's availability table: the context's own table (the
+        // node's committed placement) is neither read nor written, and the call
+        // holds the context mutex from the table upload to the answer
+        int32_t idx = -1;
+        const int rc = egpu_bestfit_query(ctx, free_core.data(), free_mem.data(), D, &req_core, &req_mem, 1, &idx);
+        if (rc != EGPU_OK) return rc;
+        if (idx < 0) return EGPU_ERR_UNSAT;
+        chosen.push_back(idx);
     }
-    // a request for 0 units of the constrained resource still needs 1 unit of the other
-    // dimension on unusable GPUs to be excluded: unusable rows are (0, 0), request >= (0, 0)
-    // would fit them, so ask for one unit of the unconstrained dimension
-    int32_t req_core = resource == EGPU_RESOURCE_CORE ? allocation_size : 1;
-    int32_t req_mem = resource == EGPU_RESOURCE_MEM ? allocation_size : 1;
-    if (resource == EGPU_RESOURCE_CORE && allocation_size > EGPU_CORE_MAX) return EGPU_ERR_UNSAT;  // >100 core = several GPUs: not v1
-    // stateless query against this request's availability table: the context's own table (the
-    // node's committed placement) is neither read nor written, and the call
-    // holds the context mutex from the table upload to the answer
-    int32_t idx = -1;
-    int rc = egpu_bestfit_query(ctx, free_core.data(), free_mem.data(), D, &req_core, &req_mem, 1, &idx);
-    if (rc != EGPU_OK) return rc;
-    if (idx < 0) return EGPU_ERR_UNSAT;
-    if (out_gpu) *out_gpu = idx;
+    if (out_gpu) *out_gpu = chosen[0];
 
-    // 4. IDs of the chosen GPU: must-include first, then ascending unit number
+    // 4. IDs of the chosen GPU(s): must-include first, then pick by pick, ascending unit number
     std::vector<char> taken(static_cast<size_t>(n_available), 0);
     int32_t n_out = 0;
     for (int64_t k = 0; k < n_must; ++k) {
@@ -124,13 +139,19 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
             out_positions[n_out++] = p;
         }
     }
-    std::vector<int32_t> cand;
-    for (int64_t i = 0; i < n_available; ++i)
-        if (gpu_of[i] == idx && !taken[i]) cand.push_back(static_cast<int32_t>(i));
-    std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) {
-        return unit_of[a] != unit_of[b] ? unit_of[a] < unit_of[b] : a < b;
-    });
-    for (size_t k = 0; k < cand.size() && n_out < allocation_size; ++k) out_positions[n_out++] = cand[k];
+    for (int32_t g : chosen) {
+        std::vector<int32_t> cand;
+        for (int64_t i = 0; i < n_available; ++i)
+            if (gpu_of[i] == g && !taken[i]) cand.push_back(static_cast<int32_t>(i));
+        std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) {
+            return unit_of[a] != unit_of[b] ? unit_of[a] < unit_of[b] : a < b;
+        });
+        // a single-GPU request takes what it still needs; a whole card gives all 100 of its units
+        const int32_t want = whole_cards ? EGPU_CORE_MAX : allocation_size;
+        int32_t have = 0;
+        for (int32_t i = 0; i < n_out; ++i) have += gpu_of[out_positions[i]] == g;
+        for (size_t k = 0; k < cand.size() && have < want && n_out < allocation_size; ++k, ++have) out_positions[n_out++] = cand[k];
+    }
     return n_out == allocation_size ? EGPU_OK : EGPU_ERR_UNSAT;
 }
 

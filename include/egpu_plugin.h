@@ -49,6 +49,11 @@ int egpu_device_id_parse(const char* id, int32_t* gpu, int64_t* unit);
  * must-include IDs first, then the lowest unit numbers of the chosen GPU; *out_gpu = the
  * GPU index.  EGPU_ERR_UNSAT when no single GPU can satisfy the request (kubelet then
  * falls back to its own choice), EGPU_ERR_PARSE on a malformed ID.
+ * Whole-card requests (gpu-core, allocation_size > 100): the reference hands such a container
+ * allocation_size / 100 whole GPUs (pkg/plugins/gpushare.go:62-69).  The size must be a multiple of
+ * 100; the GPUs are chosen one after the other, each the best fit among the cards that are still
+ * completely available (must-include GPUs first); the answer lists all 100 IDs of every chosen card,
+ * *out_gpu is the first one.
  * The context's own capacity table is not touched (the availability table of the request is
  * scored through egpu_bestfit_query), so the context that tracks the node's committed
  * placement can serve these calls too, concurrently with commits and replays. */

@@ -71,6 +71,45 @@ def conversation(stub, T, oracle_c, resource):
     got = [list(r.deviceIDs) for r in resp.container_responses]
     assert got[0] == ids(2, range(75, 100)) and got[1] == ids(1, range(0, 26)) and got[2] == ids(0, range(40, 71))
     assert got[3][:2] == ["0-55", "0-41"] and len(got[3]) == 20 and got[4] == []
+    # whole-card requests: > 100 gpu-core units = allocation_size / 100 whole GPUs (pkg/plugins/gpushare.go:62-69);
+    # cards 0, 2, 3 are completely available, card 1 is not
+    whole = ids(0, range(100)) + ids(1, range(60)) + ids(3, range(100))[::-1] + ids(2, range(100))
+    wcounts = {0: 100, 1: 60, 2: 100, 3: 100}
+    wreq = T["PreferredAllocationRequest"]()
+    cases = [(200, []), (300, []), (400, []), (250, []), (200, ["2-05"]), (200, ["3-99", "0-00"]), (200, ["1-07"])]
+    for size, must in cases:
+        c = wreq.container_requests.add()
+        c.available_deviceIDs.extend(whole)
+        c.must_include_deviceIDs.extend(must)
+        c.allocation_size = size
+    wresp = stub.get_preferred(wreq)
+    for (size, must), cresp in zip(cases, wresp.container_responses):
+        # expected: pinned cards first, then sequential best-fit picks of a full card among the cards left
+        pins = []
+        for m_ in must:
+            g = int(m_.split("-")[0])
+            if g not in pins:
+                pins.append(g)
+        chosen, ok = [], size % 100 == 0 and len(pins) <= size // 100
+        for pick in range(size // 100 if ok else 0):
+            left = {g: (n if g not in chosen and (pick < len(pins) and g == pins[pick] or pick >= len(pins) and g not in pins) else 0)
+                    for g, n in wcounts.items()}
+            g = oracle_choice(oracle_c, left, 100, resource)
+            if g < 0:
+                ok = False
+                break
+            chosen.append(g)
+        if not ok:
+            assert list(cresp.deviceIDs) == [], (size, must)
+            continue
+        exp = list(must)
+        for g in chosen:
+            exp += [s_ for s_ in ids(g, range(100)) if s_ not in must]
+        assert list(cresp.deviceIDs) == exp, (size, must)
+    got_w = [list(r.deviceIDs) for r in wresp.container_responses]
+    assert got_w[0] == ids(0, range(100)) + ids(2, range(100))                 # ties among full cards: lowest index first
+    assert got_w[1][200:] == ids(3, range(100)) and got_w[2] == [] and got_w[3] == [] and got_w[6] == []
+    assert got_w[4][0] == "2-05" and got_w[4][100:] == ids(0, range(100))      # the pinned card first, then the best of the rest
     # a malformed ID is an RPC error, as a Go handler returning (nil, err) is
     import grpc
     bad = T["PreferredAllocationRequest"]()
