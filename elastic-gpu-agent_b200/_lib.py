@@ -112,6 +112,7 @@ def load() -> C.CDLL:
         "egpu_bestfit_batches_shard_dev": (C.c_int, [vp, vp, C.c_int32, C.c_int, C.c_uint64, vp]),
         "egpu_peer_gate_dev": (C.c_int, [vp, vp]),
         "egpu_peer_gate_open": (C.c_int, [vp]),
+        "egpu_peer_gate_timeouts": (C.c_int64, [vp]),
         "egpu_bestfit_query": (C.c_int, [vp, i32p, i32p, C.c_int32, vp, vp, C.c_int64, vp]),
         "egpu_device_hash_batch": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, vp]),
         "egpu_device_hash": (C.c_int, [vp, vp, C.c_int64, vp]),

@@ -262,6 +262,10 @@ class BestFitAllocator:
     def gate_open(self):
         self._check(self._lib.egpu_peer_gate_open(self._h), "egpu_peer_gate_open")
 
+    @property
+    def gate_timeouts(self) -> int:
+        return int(self._lib.egpu_peer_gate_timeouts(self._h))
+
     def apply_deltas_dev(self, d_deltas: int, G: int, d_table_out: int = 0, commit: bool = True, stream: int | None = None):
         rc = self._lib.egpu_table_apply_deltas_dev(self._h, C.c_void_p(d_deltas), int(G),
                                                    C.c_void_p(d_table_out or None), 1 if commit else 0,

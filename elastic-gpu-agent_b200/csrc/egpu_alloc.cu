@@ -893,6 +893,19 @@ int egpu_peer_gate_dev(egpu_ctx* ctx, void* stream) {
     return EGPU_OK;
 }
 
+int64_t egpu_peer_gate_timeouts(egpu_ctx* ctx) {
+    if (!ctx) return EGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (cudaSetDevice(ctx->dev) != cudaSuccess) return EGPU_ERR_CUDA;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, reinterpret_cast<char*>(ctx->d_state) + offsetof(DevState, gate_timeouts), sizeof v,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return EGPU_ERR_CUDA;
+    }
+    return static_cast<int64_t>(v);
+}
+
 int egpu_peer_gate_open(egpu_ctx* ctx) {
     if (!ctx) return EGPU_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);

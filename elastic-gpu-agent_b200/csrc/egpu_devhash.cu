@@ -312,6 +312,13 @@ __constant__ uint32_t kSha[64] = {
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+// a + b on the FMA pipe (IMAD): in the one-lane compression chain the ALU pipe (two cycles per warp
+// instruction) is what bounds a round - ten rotations / logic ops live there - so the additions go next door
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 
 __global__ void sha256_sets_kernel(unsigned char* __restrict__ msg, const unsigned long long* __restrict__ msg_base,
                                    const unsigned long long* __restrict__ msg_len, long long n_sets,
@@ -373,7 +380,9 @@ constexpr int kShaGroup = 32;
 __global__ void __launch_bounds__(64)
 sha256_long_kernel(unsigned char* __restrict__ msg, const unsigned long long* __restrict__ msg_base,
                    const unsigned long long* __restrict__ msg_len, long long n_sets, uint32_t* __restrict__ digest) {
-    __shared__ uint32_t kw[2][kShaGroup][64];  // 16 KB: K[i] + W[i] of 2 x 32 blocks
+    // K[i] + W[i] of 2 x 32 blocks; rows padded to 65 words: lane = row writes column i into bank (row + i) mod 32 -
+    // conflict-free - and the reader's offsets are compile-time constants (no address arithmetic on its ALU pipe)
+    __shared__ uint32_t kw[2][kShaGroup][65];
     const long long s = blockIdx.x;
     if (s >= n_sets) return;
     unsigned char* m = msg + msg_base[s];
@@ -415,8 +424,7 @@ sha256_long_kernel(unsigned char* __restrict__ msg, const unsigned long long* __
                 wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
                 w[i & 15] = wi;
             }
-            // column-rotated so that the 32 lanes (rows of 64 words = the same bank) do not all hit one bank
-            out[(i + lane) & 63] = wi + kSha[i];
+            out[i] = wi + kSha[i];
         }
     };
     uint32_t h0 = 0x6a09e667, h1 = 0xbb67ae85, h2 = 0x3c6ef372, h3 = 0xa54ff53a, h4 = 0x510e527f, h5 = 0x9b05688c,
@@ -434,13 +442,13 @@ sha256_long_kernel(unsigned char* __restrict__ msg, const unsigned long long* __
                 uint32_t a = h0, b = h1, c = h2, d = h3, e = h4, f = h5, gg = h6, h = h7;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
-                    const uint32_t t0 = h + x[(i + bi) & 63];          // off the dependent path
+                    const uint32_t t0 = add_fma(h, x[i]);   // off the dependent path
                     const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
                     const uint32_t ch = (e & f) ^ (~e & gg);
-                    const uint32_t t1 = t0 + S1 + ch;
+                    const uint32_t t1 = add_fma(add_fma(t0, ch), S1);
                     const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
                     const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-                    h = gg; gg = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+                    h = gg; gg = f; f = e; e = add_fma(d, t1); d = c; c = b; b = a; a = add_fma(add_fma(t1, mj), S0);
                 }
                 h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; h5 += f; h6 += gg; h7 += h;
             }

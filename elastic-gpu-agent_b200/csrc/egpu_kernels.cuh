@@ -112,6 +112,7 @@ struct DevState {
     // launch order; a launch group (see launch_multi) never holds more than half of it.
     EpiSlot epi_multi[128];
     unsigned long long gate_epoch;        // start gates passed so far (egpu_peer_gate_dev)
+    unsigned long long gate_timeouts;     // ... of which gave up waiting (~2 s) for the host or a peer
 };
 constexpr int kEpiSlots = 32;      // ring used by pipelined launches; slot 32 = accumulate-only launches
 constexpr int kPipeGroupMax = 24;  // at most this many launches between two fully ordered ones

@@ -1001,7 +1001,7 @@ struct ApplyOuts {
 // same.  What follows the gate on the stream therefore starts within a peer-flag latency of the
 // same instant on every rank, and nothing after it waits for a host.  Epochs count up from 1;
 // a rank can be at most one gate ahead of a peer, so ">= epoch" is the arrival test.  Gives up
-// after ~2 s (peer_timeout = ~0).
+// after ~2 s (counted in DevState::gate_timeouts) and lets the stream proceed.
 __global__ void __launch_bounds__(32)
 gate_kernel(DevState* __restrict__ st, const unsigned long long* __restrict__ host_open) {
     const int world = st->peer.world, me = st->peer.rank;
@@ -1034,7 +1034,7 @@ gate_kernel(DevState* __restrict__ st, const unsigned long long* __restrict__ ho
     ok = __all_sync(0xffffffffu, ok);
     if (lane == 0) {
         st->gate_epoch = epoch;
-        if (!ok) st->peer_timeout = ~0ull;
+        if (!ok) st->gate_timeouts += 1;
     }
 }
 

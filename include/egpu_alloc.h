@@ -297,9 +297,12 @@ int egpu_bestfit_batches_shard_dev(egpu_ctx* ctx, const egpu_batch* batches, int
  * at the same time on every rank without any host in the way: launch skew between the ranks'
  * host threads no longer lands inside the sequence.  Every gate_dev needs exactly one
  * gate_open, on every rank, in the same order.  Works unattached too (host part only).
- * Gives up after ~2 s (egpu_peer_last_timeout returns -1). */
+ * A gate that has waited ~2 s gives up and lets the stream proceed (this happens when kernel
+ * launches are blocking - CUDA_LAUNCH_BLOCKING, a profiler - because the host then never gets
+ * to open it); egpu_peer_gate_timeouts counts those (synchronises the device). */
 int egpu_peer_gate_dev(egpu_ctx* ctx, void* stream);
 int egpu_peer_gate_open(egpu_ctx* ctx);
+int64_t egpu_peer_gate_timeouts(egpu_ctx* ctx);
 /* Prefix-commit (EGPU_F_PREFIX_COMMIT semantics, see egpu_bestfit_batch) over row shards.
  * The batch is the concatenation of the ranks' shards in rank order; request r of rank g
  * commits iff the running demand of its device over ALL earlier rows - the whole shards of

@@ -384,7 +384,26 @@ def test_gate_unattached_waits_for_the_host(alloc, egpu):
     assert not st.query()          # still behind the gate
     alloc.gate_open()
     st.synchronize()
-    assert int(flag.item()) == 1 and alloc.peer_last_timeout == 0
+    assert int(flag.item()) == 1 and alloc.peer_last_timeout == 0 and alloc.gate_timeouts == 0
+
+
+def test_gate_that_is_never_opened_gives_up(alloc, egpu):
+    """A gate whose host never opens it (what happens when launches are blocking) lets the stream go on after
+    ~2 s and is counted; the next gate works again."""
+    import time
+    import torch
+    alloc.set_table([1], [1])
+    st = torch.cuda.Stream()
+    t0 = time.perf_counter()
+    alloc.gate_dev(st.cuda_stream)
+    st.synchronize()
+    dt = time.perf_counter() - t0
+    assert 0.5 < dt < 10 and alloc.gate_timeouts == 1
+    alloc.gate_open()                  # the late open belongs to the gate that gave up
+    alloc.gate_dev(st.cuda_stream)
+    alloc.gate_open()
+    st.synchronize()
+    assert alloc.gate_timeouts == 1
 
 
 def test_registered_caller_memory_takes_the_zero_copy_path(alloc, oracle_c, egpu):
