@@ -61,6 +61,36 @@ int main(void) {
     CHECK(egpu_preferred_allocation(ctx, avail, n, NULL, 0, 25, EGPU_RESOURCE_CORE, pos, &gpu) == EGPU_OK, "preferred allocation");
     CHECK(gpu == 2 && strcmp(avail[pos[0]], "2-75") == 0 && strcmp(avail[pos[24]], "2-99") == 0, "preferred allocation picks the exact fit");
 
+    /* ... and it left the context's own table alone (it scores through the stateless egpu_bestfit_query) */
+    CHECK(egpu_table_size(ctx) == 8, "the tracked table survives GetPreferredAllocation");
+    CHECK(egpu_table_get(ctx, fc, fm, ov) == EGPU_OK && fc[0] == 0 && fc[1] == 75, "tracked table unchanged");
+    /* the query itself: a what-if table of two GPUs; (30, 1) fits only the second */
+    int32_t qfc[2] = {20, 40}, qfm[2] = {500, 500}, qc[2] = {30, 10}, qm[2] = {1, 1}, qi[2] = {-9, -9};
+    CHECK(egpu_bestfit_query(ctx, qfc, qfm, 2, qc, qm, 2, qi) == EGPU_OK && qi[0] == 1 && qi[1] == 0, "egpu_bestfit_query");
+    /* whole cards: 200 gpu-core units = two completely available GPUs (the reference's len/100) */
+    {
+        static char wid[300][8];
+        static const char* wav[300];
+        int wn = 0;
+        for (int g = 0; g < 3; ++g)
+            for (int j = 0; j < 100; ++j) { egpu_device_id_format(g, j, wid[wn], 8); wav[wn] = wid[wn]; ++wn; }
+        static int32_t wpos[200];
+        int32_t wg = -1;
+        CHECK(egpu_preferred_allocation(ctx, wav, wn - 50, NULL, 0, 200, EGPU_RESOURCE_CORE, wpos, &wg) == EGPU_OK, "whole-card request");
+        CHECK(wg == 0 && strcmp(wav[wpos[0]], "0-00") == 0 && strcmp(wav[wpos[199]], "1-99") == 0, "whole cards 0 and 1 (card 2 is half taken)");
+        CHECK(egpu_preferred_allocation(ctx, wav, wn - 50, NULL, 0, 300, EGPU_RESOURCE_CORE, wpos, &wg) == EGPU_ERR_UNSAT, "three whole cards are not there");
+    }
+    /* caller-owned memory pinned in place: the same call, no staging copies */
+    {
+        static int32_t rcore[4096], rmem[4096], ridx[4096];
+        for (int i = 0; i < 4096; ++i) { rcore[i] = 1 + i % 50; rmem[i] = 1 + i; ridx[i] = -9; }
+        CHECK(egpu_host_register(ctx, rcore, sizeof rcore) == EGPU_OK && egpu_host_register(ctx, rmem, sizeof rmem) == EGPU_OK &&
+              egpu_host_register(ctx, ridx, sizeof ridx) == EGPU_OK, "egpu_host_register");
+        CHECK(egpu_bestfit_batch(ctx, rcore, rmem, 4096, ridx, dc, dm, 0) == EGPU_OK && ridx[0] >= 0 && ridx[4095] >= 0, "batch on registered memory");
+        CHECK(egpu_host_unregister(ctx, rcore) == EGPU_OK && egpu_host_unregister(ctx, rmem) == EGPU_OK &&
+              egpu_host_unregister(ctx, ridx) == EGPU_OK, "egpu_host_unregister");
+    }
+
     /* types.NewDevice([...]).Hash of {"3-07"} = first 8 hex digits of sha256("3-07") */
     const char* one[1] = {"3-07"};
     char h[9];
