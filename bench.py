@@ -199,6 +199,19 @@ def workload_label(name, D, R):
     return f"{name}: {D} devices x {R} requests per GPU per step"
 
 
+def ring_batches(R):
+    """ring of device-resident batches: larger than L2 for the 1 M-row tables; 64 entries (= one full launch) for the small ones"""
+    return 2 if R > (8 << 20) else RING if R > 200_000 else MAX_BATCHES
+
+
+def l2_label(R):
+    """config.l2, identical in both arms (it describes the GPU arm's inputs; the CPU arm streams from host memory)"""
+    nb = ring_batches(R)
+    mb = nb * 12 * R / 1e6
+    return (f"GPU arm: inputs rotate through a ring of {nb} batches = {mb:.0f} MB (> 126 MB L2)" if nb * 12 * R > (126 << 20)
+            else f"GPU arm: ring of {nb} batches = {mb:.1f} MB (<= L2: small table)")
+
+
 def run_reference(args, w, e, rank, world):
     """The reference arm: the CPU implementation of the path on the host cores.  The
     reference itself has no best-fit loop and Go is not installed, so
@@ -225,10 +238,11 @@ def run_reference(args, w, e, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        # `config` is the same dict in both arms (what ran); everything descriptive lives in config_detail
         "config": {"workload": workload_label(args.workload, int(w["D"]), R), "D": int(w["D"]), "requests_per_step_per_gpu": R,
-                   "mode": "snapshot",
-                   "note": "CPU port of the builder-defined best-fit spec on the host cores (one host whatever --gpus says: R requests "
-                           "per step); the reference repo has no such loop and no Go toolchain is present"},
+                   "mode": "snapshot", "l2": l2_label(R)},
+        "config_detail": {"note": "CPU port of the builder-defined best-fit spec on the host cores (one host whatever --gpus says: R requests "
+                                  "per step); the reference repo has no such loop and no Go toolchain is present"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {R} requests, OpenMP over request rows"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,8 +263,7 @@ class Leg:
         self.D, self.R = int(self.w["D"]), int(self.w["R"])
         self.rank, self.world, self.dev = rank, world, dev
         D, R = self.D, self.R
-        # ring: larger than L2 for the 1 M-row tables; 64 entries (= one full launch) for the small ones
-        self.nb = 2 if R > (8 << 20) else RING if R > 200_000 else MAX_BATCHES
+        self.nb = ring_batches(R)
         self.ring = []
         for b in range(self.nb):
             c = torch.empty(R, dtype=torch.int32, device=dev)
@@ -824,10 +837,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "timing": timing, "wall_ms_per_step_back_to_back": (wall_ms / K) if wall_ms else None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_label(args.workload, D, R),
-                       "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
-                       "l2": f"inputs rotate through a ring of {nb} batches = {nb * 12 * R / 1e6:.0f} MB (> 126 MB L2)"
-                             if nb * 12 * R > (126 << 20) else f"ring of {nb} batches = {nb * 12 * R / 1e6:.1f} MB",
+            "config": {"workload": workload_label(args.workload, D, R), "D": D, "requests_per_step_per_gpu": R, "mode": "snapshot",
+                       "l2": l2_label(R)},
+            "config_detail": {
                        "launch": ("eager: scan launch + NCCL all-gather + apply_deltas launch per step" if use_nccl else
                                   f"the {K} steps = {n_scan} multi-batch scan launch(es) of up to {MAX_BATCHES} batches (egpu_bestfit_batches"
                                   f"{'_shard' if use_peer else ''}_dev) in one CUDA graph" +
