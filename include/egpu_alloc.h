@@ -24,6 +24,12 @@
  *       pkg/common/const.go:4 (GPUPercentEachCard = 100) and the vendored
  *       resource names elasticgpu.io/gpu-core, elasticgpu.io/gpu-memory
  *       (vendor/elasticgpu.io/elastic-gpu/api/v1alpha1/types.go:105-112).
+ *   egpu_bestfit_batches_dev / egpu_bestfit_query
+ *       the same slot, for a caller with several requests' worth of batches in
+ *       hand (one launch for up to 64 of them), and for the stateless what-if
+ *       form GetPreferredAllocation needs (pkg/plugins/base.go:94-96: kubelet
+ *       passes the available IDs of ONE admission; the node's committed table
+ *       must not be touched by it).
  *   egpu_replay
  *       commits serialised under baseDevicePlugin.lock in PreStartContainer
  *       (pkg/plugins/gpushare.go:114,239) and frees issued by
@@ -133,7 +139,8 @@ int  egpu_backend(egpu_ctx* ctx);
 int64_t egpu_launch_count(egpu_ctx* ctx);
 int  egpu_set_variant(egpu_ctx* ctx, int variant);
 /* ABI version: major*1000 + minor.  Minor revisions only add entry points (1.1 placement
- * restore, 1.2 prefix-commit over row shards, 1.3 rounds); a caller built against 1.0 keeps
+ * restore, 1.2 prefix-commit over row shards, 1.3 rounds, 1.4 multi-batch launches, stateless query,
+ * start gate, host registration); a caller built against 1.0 keeps
  * working. */
 int  egpu_abi_version(void);
 
