@@ -12,7 +12,7 @@ table (`--exchange nccl` is the literal all-gather form, kept for
 
 The K steps of the timed region are issued the way a caller with K batches in hand issues
 them: as multi-batch launches (egpu_bestfit_batches_dev, up to 64 batches per launch - one
-launch latency, one ramp and one tail for the lot).  The region is replayed REPLAYS times;
+launch latency, one ramp and one tail for the lot).  The region is replayed REPLAYS (101) times;
 every replay is bracketed by a barrier + device synchronisation, starts behind a device-side
 start gate (so host launch skew is outside every rank's window), is timed with CUDA events
 on the launching stream and reduced with MAX over the ranks; `ms_per_step` is the median
@@ -53,7 +53,7 @@ import numpy as np  # noqa: E402
 METRIC = "alloc_decisions_per_sec"
 UNIT = "decisions/s"
 MAX_BATCHES = 64  # EGPU_MAX_BATCHES: batches per multi-batch launch
-REPLAYS = int(os.environ.get("EGPU_BENCH_REPLAYS", "31"))
+REPLAYS = int(os.environ.get("EGPU_BENCH_REPLAYS", "101"))
 # under a profiler that serialises launches (ncu) the start gate cannot work - it waits for a host that is
 # stuck in the gate's own launch - and would sit there until its 2 s timeout: EGPU_BENCH_NO_GATE=1 leaves it out
 USE_GATE = [not os.environ.get("EGPU_BENCH_NO_GATE")]
