@@ -723,10 +723,13 @@ lut_build_kernel(const DevState* __restrict__ st, DevLut* __restrict__ lut) {
 // (Measured and dropped, DESIGN.md 7.2: round 1's three conditional adds into one table per warp;
 // 64-bit sums in columns owned by lane pairs with the half-warps taking turns - fewer shared-memory
 // wavefronts, 7.95 M against 10.3 M per 20 M decisions, but 8.3 KB per warp halves the occupancy.)
-constexpr int kLutFlushTrips = 32;
+// (4 copies of 8 lanes would fit four CTAs per SM instead of three: measured slower, 2.97 against 2.77 us per
+// batch - the extra bank conflicts of the adds cost more than the occupancy brings)
 constexpr int kLutCopies = 8;
-constexpr int kLutPlane = kMaxD + 4;                 // 64 devices + one dummy word per lane of the copy
-constexpr int kLutCopyStride = 2 * kLutPlane + 4;    // 140 words = 12 banks
+constexpr int kLutLanesPerCopy = 32 / kLutCopies;
+constexpr int kLutFlushTrips = 32;                                // 12-bit field, <= 3 per add, 4 lanes x 8 rows per trip
+constexpr int kLutPlane = kMaxD + kLutLanesPerCopy;               // 64 devices + one dummy word per lane of the copy
+constexpr int kLutCopyStride = 2 * kLutPlane + 4;                 // 140 words = 12 banks
 template <int THREADS>
 struct LutSmem {
     DevLut lut;
@@ -787,8 +790,8 @@ __device__ __forceinline__ int lut_scan_rows(LutSmem<THREADS>& sm, DevState* __r
     __syncthreads();
     const DevLut& L = sm.lut;
     uint32_t* const hw = &sm.hist32[warp][0];
-    uint32_t* const hcopy = hw + (lane >> 2) * kLutCopyStride;
-    const uint32_t dummy_col = static_cast<uint32_t>(kMaxD) + (static_cast<uint32_t>(lane) & 3u);
+    uint32_t* const hcopy = hw + (lane / kLutLanesPerCopy) * kLutCopyStride;
+    const uint32_t dummy_col = static_cast<uint32_t>(kMaxD) + (static_cast<uint32_t>(lane) % kLutLanesPerCopy);
 
     // device (0..63) or 0xFF for one request: two dependent shared-memory reads, no branch
     // (the read of ovf[] is predicated: only requests whose bucket holds several thresholds)
