@@ -7,8 +7,9 @@
 // Layout in HBM:
 //   req_core[R], req_mem[R]  int32, SoA, 16-byte aligned  (read once, 128-bit)
 //   out_idx[R]               int32, 16-byte aligned       (written once, 128-bit)
-//   DevState                 one 2 KiB block: table (free_core, free_mem,
-//                            oversub), running int64 demand sums, ticket
+//   DevState                 ~170 KB: table (free_core, free_mem, oversub), its sorted
+//                            view, epilogue slots (running int64 demand sums + arrival
+//                            ticket per launch / per batch), peer configuration
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,8 +1,9 @@
 // egpu_scan.cuh — snapshot-mode kernels of the best-fit path (sm_100a): the register scan
-// (bestfit_sorted_kernel), its packed-format twin, the literal grid scan, the lookup-table
-// scan for large D with its table builder, the shared epilogue (demand sums, arrival ticket,
-// last-CTA publication, fused peer push) and the two apply kernels.  Included by
-// egpu_alloc.cu only; see DESIGN.md §4.
+// (bestfit_sorted_kernel and its multi-batch form), its packed-format twin, the literal grid
+// scan, the lookup-table scan for large D (single- and multi-batch) with its table builder, the
+// shared epilogue (demand sums, arrival ticket, last-CTA publication, fused peer push / apply),
+// the exchange-word helpers, the apply kernels, the start gate, and the prefix-commit and
+// rounds kernels.  Included by egpu_alloc.cu only; see DESIGN.md §4, §5.
 #pragma once
 #include <type_traits>
 #include "egpu_kernels.cuh"
