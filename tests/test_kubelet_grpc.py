@@ -52,13 +52,13 @@ def conversation(stub, T, oracle_c, resource):
     available = ids(0, range(40, 100)) + ids(2, range(75, 100))[::-1] + ids(1, range(0, 30))
     counts = {0: 60, 1: 30, 2: 25}
     req = T["PreferredAllocationRequest"]()
-    for size, must in ((25, []), (26, []), (31, []), (20, ["0-55", "0-41"]), (61, [])):
+    for size, must in ((25, []), (26, []), (31, []), (20, ["0-55", "0-41"]), (61, []), (10, [])):
         c = req.container_requests.add()
         c.available_deviceIDs.extend(available)
         c.must_include_deviceIDs.extend(must)
         c.allocation_size = size
     resp = stub.get_preferred(req)
-    assert len(resp.container_responses) == 5
+    assert len(resp.container_responses) == 6
     for cresp, creq in zip(resp.container_responses, req.container_requests):
         must = list(creq.must_include_deviceIDs)
         pinned = int(must[0].split("-")[0]) if must else None
@@ -71,6 +71,7 @@ def conversation(stub, T, oracle_c, resource):
     got = [list(r.deviceIDs) for r in resp.container_responses]
     assert got[0] == ids(2, range(75, 100)) and got[1] == ids(1, range(0, 26)) and got[2] == ids(0, range(40, 71))
     assert got[3][:2] == ["0-55", "0-41"] and len(got[3]) == 20 and got[4] == []
+    assert got[5] == ids(2, range(75, 85))                      # a part of a GPU offered in descending order: lowest units first
     # whole-card requests: > 100 gpu-core units = allocation_size / 100 whole GPUs (pkg/plugins/gpushare.go:62-69);
     # cards 0, 2, 3 are completely available, card 1 is not
     whole = ids(0, range(100)) + ids(1, range(60)) + ids(3, range(100))[::-1] + ids(2, range(100))
