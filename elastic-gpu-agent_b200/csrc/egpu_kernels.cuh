@@ -108,6 +108,7 @@ struct DevState {
         unsigned long long acc[2 * kMaxD];  // running batch sums: core[0..63], mem[64..127]
         unsigned int ticket;
         unsigned int pad_[3];
+        unsigned int pair[kMaxD];           // plain-snapshot epilogue: the two finishers of a device meet here
     } epi[33];
     // Multi-batch launches (egpu_bestfit_batches_dev): one slot per BATCH, taken from this ring in
     // launch order; a launch group (see launch_multi) never holds more than half of it.
@@ -121,6 +122,9 @@ constexpr int kMultiSlots = 128;   // DevState::epi_multi
 constexpr int kMultiMax = 64;      // batches per multi-batch launch (descriptors travel as kernel parameters)
 
 // One batch of a multi-batch launch: the arguments of egpu_bestfit_batch_dev, per batch.
+// plain-snapshot epilogue: bits 49..63 of a running sum count the CTAs that have added to it
+constexpr int kEpiTicketShift = 49;
+
 struct BatchDesc {
     const int32_t* rc;
     const int32_t* rm;

@@ -198,6 +198,39 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
     // write ITS table' to table_out: no separate apply launches, no second stream
     const unsigned long long lag = ec.lag;
     const int tid = threadIdx.x;
+    if ((flags & (kFlagFinalize | kFlagCommit)) == kFlagFinalize && !push && !tile_sums && ec.n_tiles < (1 << (64 - kEpiTicketShift))) {
+        // Plain snapshot (no commit, no exchange): the arrival ticket rides in the top bits of every
+        // running sum, so ONE returning atomic per word is the whole protocol: the CTA whose add
+        // returns n_tiles - 1 arrivals holds that word's total (old + own) and writes it out.  Nothing
+        // is re-read, so nothing needs a fence; the words of one batch may be finished by different
+        // CTAs.  Only the oversubscription flag needs both sums of a device: the two finishers swap
+        // their sign bits through ep.pair[d] (the second one to come writes the flag).  Critical
+        // path of a launch's last CTA: one L2 round trip (two with table'), against red + fence +
+        // ticket + re-load in the general path below.  Sums < 2^49 (EGPU_MAX_ROWS rows of < 2^18).
+        if (tid >= 2 * D) return;
+        const int d = tid < D ? tid : tid - D;
+        const int j = tid < D ? core_off + tid : mem_off + (tid - D);
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) tot += wacc[w * wstride + j];
+        unsigned long long* word = &ep.acc[tid < D ? tid : kMaxD + d];
+        const unsigned long long old = atomicAdd(word, tot + (1ull << kEpiTicketShift));
+        if ((old >> kEpiTicketShift) != static_cast<unsigned long long>(ec.n_tiles - 1)) return;
+        *reinterpret_cast<volatile unsigned long long*>(word) = 0ull;  // the slot's next batch is at least a launch group away
+        const long long total = static_cast<long long>((old + tot) & ((1ull << kEpiTicketShift) - 1));
+        if (delta_out) delta_out[tid] = total;
+        if (table_out) {
+            const long long left = static_cast<long long>(tid < D ? st->free_core[d] : st->free_mem[d]) - total;
+            table_out[tid] = sat_i32(left);
+            const unsigned int mine = 2u | (left < 0 ? 1u : 0u);
+            const unsigned int other = atomicExch(&ep.pair[d], mine);
+            if (other & 2u) {
+                table_out[2 * D + d] = static_cast<int32_t>((other | mine) & 1u);
+                *reinterpret_cast<volatile unsigned int*>(&ep.pair[d]) = 0u;
+            }
+        }
+        return;
+    }
     if (tid < 2 * D) {
         const int j = tid < D ? core_off + tid : mem_off + (tid - D);
         unsigned long long tot = 0;
