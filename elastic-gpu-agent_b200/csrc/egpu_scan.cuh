@@ -114,21 +114,45 @@ __device__ __forceinline__ void hist_add(SnapSmem<DT, THREADS>& s, int warp, int
         static_cast<unsigned long long>(static_cast<uint32_t>(mem));
 }
 
-// ---- exchange rows (XchgRow): push one device's two sums to every peer, pull and consume ----
-// thread d < D of one CTA; (dc, dm) = this rank's demand on device d under exchange step step_plus1 - 1
-__device__ __forceinline__ void xchg_push(DevState* st, unsigned long long step_plus1, int d, int D, long long dc, long long dm) {
+// ---- exchange rows (XchgRow): push this rank's sums to every peer, pull and consume ----
+// word w of the 2*D-word vector (w = d: core demand on device d, w = D + d: mem demand): value v of this rank
+// under exchange step step_plus1 - 1, to every rank's buffer.  Every 16-byte store is two 8-byte
+// single-copy-atomic words with their own tags, so the words of a vector can come from different threads/CTAs.
+__device__ __forceinline__ void xchg_push_word(DevState* st, unsigned long long step_plus1, int w, long long v) {
     const int world = st->peer.world, me = st->peer.rank;
     const int xs = static_cast<int>((step_plus1 - 1) % kXchgSlots);
     const unsigned long long tag = static_cast<unsigned long long>(xchg_tag(step_plus1)) << 32;
-    const unsigned long long c = static_cast<unsigned long long>(dc), m = static_cast<unsigned long long>(dm);
-    const ulonglong2 wc = make_ulonglong2(tag | (c & 0xffffffffull), tag | (c >> 32));
-    const ulonglong2 wm = make_ulonglong2(tag | (m & 0xffffffffull), tag | (m >> 32));
+    const unsigned long long u = static_cast<unsigned long long>(v);
+    const ulonglong2 wv = make_ulonglong2(tag | (u & 0xffffffffull), tag | (u >> 32));
     for (int p = 0; p < world; ++p) {
         XchgRow& row = st->peer.buf[p]->slot[xs][me];
-        // two 16-byte stores (each half is an 8-byte single-copy-atomic word with its own tag)
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&row.ll[2 * d]), "l"(wc.x), "l"(wc.y) : "memory");
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&row.ll[2 * (D + d)]), "l"(wm.x), "l"(wm.y) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(&row.ll[2 * w]), "l"(wv.x), "l"(wv.y) : "memory");
     }
+}
+// thread d < D of one CTA; (dc, dm) = this rank's demand on device d
+__device__ __forceinline__ void xchg_push(DevState* st, unsigned long long step_plus1, int d, int D, long long dc, long long dm) {
+    xchg_push_word(st, step_plus1, d, dc);
+    xchg_push_word(st, step_plus1, D + d, dm);
+}
+// waits until word w of every rank g carries the step's tag; adds those of ranks [g_lo, g_hi) into v;
+// zeroes the words (consumed).  false = gave up after ~2 s (a rank died).
+__device__ __forceinline__ bool xchg_pull_word(XchgRow* rows, int world, unsigned long long step_plus1, int w, int g_lo, int g_hi,
+                                               long long& v) {
+    const unsigned long long tag = xchg_tag(step_plus1);
+    const long long t0 = clock64();
+    for (int g = 0; g < world; ++g) {
+        unsigned long long* pw = &rows[g].ll[2 * w];
+        unsigned long long w0, w1;
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(pw) : "memory");
+            if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+            if (clock64() - t0 > 4000000000ll) return false;
+            __nanosleep(40);
+        }
+        if (g >= g_lo && g < g_hi) v += static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32));
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pw), "l"(0ull) : "memory");
+    }
+    return true;
 }
 // thread d < D: waits until rank g's two values for device d carry the step's tag, for every rank g
 // of the world; adds those of ranks [g_lo, g_hi) into (dc, dm); zeroes the words (consumed: a replayed
@@ -198,12 +222,14 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
     // write ITS table' to table_out: no separate apply launches, no second stream
     const unsigned long long lag = ec.lag;
     const int tid = threadIdx.x;
-    if ((flags & (kFlagFinalize | kFlagCommit)) == kFlagFinalize && !push && !tile_sums && ec.n_tiles < (1 << (64 - kEpiTicketShift))) {
-        // Plain snapshot (no commit, no exchange): the arrival ticket rides in the top bits of every
-        // running sum, so ONE returning atomic per word is the whole protocol: the CTA whose add
-        // returns n_tiles - 1 arrivals holds that word's total (old + own) and writes it out.  Nothing
-        // is re-read, so nothing needs a fence; the words of one batch may be finished by different
-        // CTAs.  Only the oversubscription flag needs both sums of a device: the two finishers swap
+    if ((flags & (kFlagFinalize | kFlagCommit)) == kFlagFinalize && !lag && !tile_sums && ec.n_tiles < (1 << (64 - kEpiTicketShift))) {
+        // Plain snapshot (no commit, no lagged apply): the arrival ticket rides in the top bits of
+        // every running sum, so ONE returning atomic per word is the whole protocol: the CTA whose
+        // add returns n_tiles - 1 arrivals holds that word's total (old + own) and publishes it.
+        // Nothing is re-read, so nothing needs a fence; the words of one batch may be finished by
+        // different CTAs.  The exchange is word-granular too (every pushed word carries its own
+        // tag): the finisher of a word pushes it and, with apply_now, collects that word from every
+        // rank.  Only the oversubscription flag needs both sums of a device: the two finishers swap
         // their sign bits through ep.pair[d] (the second one to come writes the flag).  Critical
         // path of a launch's last CTA: one L2 round trip (two with table'), against red + fence +
         // ticket + re-load in the general path below.  Sums < 2^49 (EGPU_MAX_ROWS rows of < 2^18).
@@ -217,11 +243,23 @@ __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc,
         const unsigned long long old = atomicAdd(word, tot + (1ull << kEpiTicketShift));
         if ((old >> kEpiTicketShift) != static_cast<unsigned long long>(ec.n_tiles - 1)) return;
         *reinterpret_cast<volatile unsigned long long*>(word) = 0ull;  // the slot's next batch is at least a launch group away
-        const long long total = static_cast<long long>((old + tot) & ((1ull << kEpiTicketShift) - 1));
+        long long total = static_cast<long long>((old + tot) & ((1ull << kEpiTicketShift) - 1));
         if (delta_out) delta_out[tid] = total;
+        bool ok = true;
+        if (push) {
+            xchg_push_word(st, push, tid, total);  // word tid of this rank's vector, straight into every rank's buffer
+            if (ec.apply_now) {
+                // the ranks run the same launch at the same time (start gate): a peer-store latency.
+                // This thread has pushed before it waits and no push waits for anything: no cycle.
+                total = 0;
+                ok = xchg_pull_word(st->peer.buf[st->peer.rank]->slot[(push - 1) % kXchgSlots], st->peer.world, push, tid, 0,
+                                    st->peer.world, total);
+                if (!ok) st->peer_timeout = push;  // a rank died: reported by the host, table' is not written
+            }
+        }
         if (table_out) {
             const long long left = static_cast<long long>(tid < D ? st->free_core[d] : st->free_mem[d]) - total;
-            table_out[tid] = sat_i32(left);
+            if (ok) table_out[tid] = sat_i32(left);
             const unsigned int mine = 2u | (left < 0 ? 1u : 0u);
             const unsigned int other = atomicExch(&ep.pair[d], mine);
             if (other & 2u) {
