@@ -18,6 +18,7 @@ for tool in memcheck racecheck synccheck; do
   run $tool multi python -m pytest tests/test_gpu_multi.py -q -x -m gpu -k "$SUB_A"
   run $tool parity python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "$SUB_B"
 done
+[ -n "${SKIP_DEVHASH:-}" ] && { run memcheck world2 python -m pytest tests/test_gpu_peer_exchange.py -q -x -m gpu -k "world2_two_processes_one_gpu or world1"; exit 0; }
 run memcheck devhash python -m pytest tests/test_devhash.py tests/test_restore.py -q -x -m gpu
 run memcheck world2 python -m pytest tests/test_gpu_peer_exchange.py -q -x -m gpu -k "world2_two_processes_one_gpu or world1"
 run racecheck devhash python -m pytest tests/test_devhash.py -q -x -m gpu -k "long_messages or golden_batch"
