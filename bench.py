@@ -916,7 +916,7 @@ def next_rows(torch, e, alloc, stream, dev):
     flat, id_off, set_off = devhash.flatten(sets)             # marshalling is not timed on either side
     flat_l, id_off_l, set_off_l = devhash.flatten([req] + sets)
     dt_h = dt_l = None
-    for _ in range(2):  # the first full-size call grows the context's device arena: best of two
+    for _ in range(4):  # the first full-size call grows the context's device arena and the driver's staging: best of four
         t0 = time.perf_counter()
         hs = devhash.device_hashes_flat(alloc, flat, id_off, set_off)
         dt = time.perf_counter() - t0

@@ -30,7 +30,8 @@ constexpr int kSortItems = 8;                          // items per thread (bloc
 constexpr int kSortTile = kSortThreads * kSortItems;   // items per CTA per pass
 
 struct HashErr {
-    int bad;  // != 0: some ID is empty, longer than 16 bytes or has a foreign character
+    int bad;      // != 0: some ID is empty, longer than 16 bytes, outside the byte buffer or has a foreign character
+    int max_len;  // longest ID of the batch: the number of key digits the sort has to look at
 };
 
 __device__ __forceinline__ uint32_t char_code(unsigned char c) {
@@ -40,14 +41,31 @@ __device__ __forceinline__ uint32_t char_code(unsigned char c) {
 }
 __device__ __forceinline__ char code_char(uint32_t n) { return n == 1u ? '-' : static_cast<char>('0' + (n - 2u)); }
 
-__global__ void pack_ids_kernel(const char* __restrict__ flat, const long long* __restrict__ id_off, long long n_ids,
-                                unsigned long long* __restrict__ key, uint32_t* __restrict__ len1, HashErr* err) {
+// Also the validation of the caller's offsets (every ID 1..16 bytes, inside the byte buffer), the set
+// index of every ID (binary search in the few set offsets) and the longest ID: the host never walks
+// the n_ids-long arrays, it only hands them to the copy engine.
+__global__ void pack_ids_kernel(const char* __restrict__ flat, long long flat_bytes, const long long* __restrict__ id_off,
+                                long long n_ids, const long long* __restrict__ set_off, long long n_sets,
+                                unsigned long long* __restrict__ key, uint32_t* __restrict__ set, uint32_t* __restrict__ len1,
+                                HashErr* err) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_ids) return;
-    const long long b = id_off[i], e = id_off[i + 1];
+    const bool live = i < n_ids;
+    const long long b = live ? id_off[i] : 0, e = live ? id_off[i + 1] : 1;
     const long long l = e - b;
+    const int my_len = live && l >= 1 && l <= 16 ? static_cast<int>(l) : 0;
+    const int warp_max = __reduce_max_sync(0xffffffffu, my_len);
+    if ((threadIdx.x & 31) == 0 && warp_max) atomicMax(&err->max_len, warp_max);
+    if (!live) return;
+    {   // set of ID i: the last q with set_off[q] <= i (empty sets share their offset with the next one)
+        long long lo = 0, hi = n_sets;  // invariant: set_off[lo] <= i < set_off[hi]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (set_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        set[i] = static_cast<uint32_t>(lo);
+    }
     unsigned long long k = 0;
-    bool ok = l >= 1 && l <= 16;
+    bool ok = l >= 1 && l <= 16 && b >= 0 && e <= flat_bytes;
     for (int j = 0; j < 16; ++j) {
         uint32_t code = 0;
         if (j < l && ok) {
@@ -212,14 +230,35 @@ scan_block_sums_kernel(const uint32_t* __restrict__ v, long long n, unsigned lon
         if (threadIdx.x == 0) block_sum[blockIdx.x] = x;
     }
 }
-__global__ void scan_serial_kernel(unsigned long long* __restrict__ a, long long n) {  // n = #blocks, small
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long run = 0;
-        for (long long i = 0; i < n; ++i) {
-            const unsigned long long v = a[i];
-            a[i] = run;
-            run += v;
+// exclusive scan of the block sums, in place: one CTA, 1024 values per trip
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* __restrict__ a, long long n) {
+    __shared__ unsigned long long warp_sum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long val = i < n ? a[i] : 0ull;
+        unsigned long long x = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
         }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        if (i < n) a[i] = carry + x + (warp ? warp_sum[warp - 1] : 0ull) - val;
+        carry += warp_sum[31];
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(1024)
@@ -536,17 +575,10 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
     if (n_sets > (1ll << 24) || n_ids > (1ll << 31) - 1) return EGPU_ERR_INVALID;
     const int64_t flat_bytes = id_offsets[n_ids];
     if (flat_bytes < 0 || (flat_bytes > 0 && !ids_flat)) return EGPU_ERR_INVALID;
-    std::vector<uint32_t> set_of(static_cast<size_t>(n_ids));
-    int64_t max_len = 0;
-    for (int64_t q = 0; q < n_sets; ++q) {
+    for (int64_t q = 0; q < n_sets; ++q)
         if (set_offsets[q + 1] < set_offsets[q]) return EGPU_ERR_INVALID;
-        for (int64_t i = set_offsets[q]; i < set_offsets[q + 1]; ++i) set_of[i] = static_cast<uint32_t>(q);
-    }
-    for (int64_t i = 0; i < n_ids; ++i) {
-        const int64_t l = id_offsets[i + 1] - id_offsets[i];
-        if (l < 1 || l > 16) return EGPU_ERR_PARSE;
-        max_len = l > max_len ? l : max_len;
-    }
+    // the n_ids-long arrays are not walked here: lengths, bounds, set membership and the longest ID
+    // come from pack_ids_kernel (a pageable 1 M-ID batch spent more host time on that than the GPU on the sort)
     const size_t n = static_cast<size_t>(n_ids);
     const int64_t tiles = (n_ids + kSortTile - 1) / kSortTile;
     const size_t msg_cap = static_cast<size_t>(flat_bytes) + n + static_cast<size_t>(n_sets) * 128 + 64;
@@ -566,21 +598,26 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
     if (flat_bytes) EGPU_CUDA(ctx, cudaMemcpyAsync(r.flat.p, ids_flat, flat_bytes, cudaMemcpyHostToDevice, s));
     EGPU_CUDA(ctx, cudaMemcpyAsync(r.id_off.p, id_offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
     EGPU_CUDA(ctx, cudaMemcpyAsync(r.set_off.p, set_offsets, sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice, s));
-    if (n) EGPU_CUDA(ctx, cudaMemcpyAsync(r.set_a.p, set_of.data(), 4 * n, cudaMemcpyHostToDevice, s));
     unsigned long long* ka = r.key_a.as<unsigned long long>();
     unsigned long long* kb = r.key_b.as<unsigned long long>();
     uint32_t* sa = r.set_a.as<uint32_t>();
     uint32_t* sb = r.set_b.as<uint32_t>();
     const unsigned nb256 = static_cast<unsigned>((n_ids + 255) / 256);
     if (n) {
-        pack_ids_kernel<<<nb256, 256, 0, s>>>(r.flat.as<char>(), r.id_off.as<long long>(), n_ids, ka, r.len1.as<uint32_t>(),
-                                              r.err.as<HashErr>());
+        pack_ids_kernel<<<nb256, 256, 0, s>>>(r.flat.as<char>(), flat_bytes, r.id_off.as<long long>(), n_ids,
+                                              r.set_off.as<long long>(), n_sets, ka, sa, r.len1.as<uint32_t>(), r.err.as<HashErr>());
         ctx->launches += 1;
+        HashErr first{0, 0};
+        EGPU_CUDA(ctx, cudaMemcpyAsync(&first, r.err.p, sizeof first, cudaMemcpyDeviceToHost, s));
+        EGPU_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->prev_is_scan = false;
+        if (first.bad) return EGPU_ERR_PARSE;
+        const int max_len = first.max_len;
         // LSD: last character first, then the set index
         int set_digits = 0;
         while ((1ll << (4 * set_digits)) < n_sets) ++set_digits;
         std::vector<int> shifts;
-        for (int j = static_cast<int>(max_len) - 1; j >= 0; --j) shifts.push_back(60 - 4 * j);
+        for (int j = max_len - 1; j >= 0; --j) shifts.push_back(60 - 4 * j);
         for (int j = 0; j < set_digits; ++j) shifts.push_back(64 + 4 * j);
         for (int shift : shifts) {
             radix_hist_kernel<<<static_cast<unsigned>(tiles), kSortThreads, 0, s>>>(ka, sa, n_ids, shift, r.hist.as<uint32_t>());
@@ -594,13 +631,13 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
     }
     r.sorted_key = ka;
     r.sorted_set = sa;
-    HashErr herr{0};
+    HashErr herr{0, 0};
     if (need_digest) {
         const unsigned nblk = static_cast<unsigned>((n_ids + 1023) / 1024);
         if (n) {
             sorted_len_kernel<<<nb256, 256, 0, s>>>(ka, n_ids, r.len1.as<uint32_t>());
             scan_block_sums_kernel<<<nblk, 1024, 0, s>>>(r.len1.as<uint32_t>(), n_ids, r.blk.as<unsigned long long>());
-            scan_serial_kernel<<<1, 32, 0, s>>>(r.blk.as<unsigned long long>(), nblk);
+            scan_blocks_kernel<<<1, 1024, 0, s>>>(r.blk.as<unsigned long long>(), nblk);
             scan_apply_kernel<<<nblk, 1024, 0, s>>>(r.len1.as<uint32_t>(), n_ids, r.blk.as<unsigned long long>(),
                                                     r.pref.as<unsigned long long>());
             ctx->launches += 4;

@@ -7,6 +7,7 @@ import json
 import os
 import random
 
+import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -139,3 +140,26 @@ def test_cuda_rejects_foreign_ids(bad, alloc, egpu):
     with pytest.raises(egpu.EgpuError) as ei:
         devhash.device_hashes(alloc, [bad])
     assert ei.value.code == -7
+
+
+@pytest.mark.gpu
+def test_cuda_empty_sets_between_full_ones_and_bad_offsets(alloc, egpu):
+    """The set index of every ID comes from a binary search in the set offsets on the device: empty sets
+    (equal offsets) at the start, in the middle, doubled and at the end must not shift their neighbours.
+    Offsets that run backwards or past the byte buffer are a parse error, not a wild read."""
+    import hashlib
+    import random
+    from elastic_gpu_agent_b200 import devhash
+    rng = random.Random(5)
+    sets = [[], ["3-07", "3-01"], [], [], ["0-%02d" % j for j in rng.sample(range(5000), 700)], ["12-345"], [], []]
+    exp = [hashlib.sha256(":".join(sorted(x)).encode()).hexdigest()[:8] for x in sets]
+    assert devhash.device_hashes(alloc, sets) == exp
+    assert devhash.locate(alloc, ["3-01", "3-07"], sets) == 1
+    assert devhash.locate(alloc, [], sets) == 0
+    flat, id_off, set_off = devhash.flatten([["0-01", "0-02", "0-03"]])
+    for bad in ([0, 4, 2, 12], [0, 4, 20, 12], [0, -4, 8, 12]):
+        off = np.array(bad, dtype=np.int64)
+        with pytest.raises(egpu.EgpuError) as ei:
+            devhash.device_hashes_flat(alloc, flat, off, set_off)
+        assert ei.value.code in (-7, -1), bad
+    assert devhash.device_hashes_flat(alloc, flat, id_off, set_off) == [hashlib.sha256(b"0-01:0-02:0-03").hexdigest()[:8]]
