@@ -135,51 +135,46 @@ __device__ __forceinline__ void xchg_push(DevState* st, unsigned long long step_
     xchg_push_word(st, step_plus1, D + d, dm);
 }
 // waits until word w of every rank g carries the step's tag; adds those of ranks [g_lo, g_hi) into v;
-// zeroes the words (consumed).  false = gave up after ~2 s (a rank died).
+// zeroes the words (consumed: a replayed sequence pushes the same steps again).  false = gave up after
+// ~2 s (a rank died).  The loads of four ranks at a time are issued together (they are independent): the
+// wait is one or two L2 round trips after the last word has landed, not one per rank.  Four, not eight:
+// this is inlined into the scans' epilogues and must stay inside their register budget (eight ranks'
+// words in flight took the 8-device scan from 60 to 88 registers and a quarter of its throughput).
+constexpr int kPullGroup = 4;
 __device__ __forceinline__ bool xchg_pull_word(XchgRow* rows, int world, unsigned long long step_plus1, int w, int g_lo, int g_hi,
                                                long long& v) {
     const unsigned long long tag = xchg_tag(step_plus1);
     const long long t0 = clock64();
-    for (int g = 0; g < world; ++g) {
-        unsigned long long* pw = &rows[g].ll[2 * w];
-        unsigned long long w0, w1;
+    for (int gb = 0; gb < world; gb += kPullGroup) {
+        const int ng = world - gb < kPullGroup ? world - gb : kPullGroup;
+        unsigned int pending = (1u << ng) - 1u;
         for (;;) {
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(pw) : "memory");
-            if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+            unsigned long long w0[kPullGroup], w1[kPullGroup];
+#pragma unroll
+            for (int k = 0; k < kPullGroup; ++k) {
+                w0[k] = w1[k] = 0ull;
+                if ((pending >> k) & 1u)
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[k]), "=l"(w1[k]) : "l"(&rows[gb + k].ll[2 * w]) : "memory");
+            }
+#pragma unroll
+            for (int k = 0; k < kPullGroup; ++k) {
+                if (((pending >> k) & 1u) && (w0[k] >> 32) == tag && (w1[k] >> 32) == tag) {
+                    if (gb + k >= g_lo && gb + k < g_hi) v += static_cast<long long>((w0[k] & 0xffffffffull) | (w1[k] << 32));
+                    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(&rows[gb + k].ll[2 * w]), "l"(0ull) : "memory");
+                    pending &= ~(1u << k);
+                }
+            }
+            if (!pending) break;
             if (clock64() - t0 > 4000000000ll) return false;
             __nanosleep(40);
         }
-        if (g >= g_lo && g < g_hi) v += static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32));
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pw), "l"(0ull) : "memory");
     }
     return true;
 }
-// thread d < D: waits until rank g's two values for device d carry the step's tag, for every rank g
-// of the world; adds those of ranks [g_lo, g_hi) into (dc, dm); zeroes the words (consumed: a replayed
-// sequence pushes the same steps again).  false = gave up after ~2 s (a rank died).
+// thread d < D: the two values for device d (words d and D + d) of every rank; see xchg_pull_word
 __device__ __forceinline__ bool xchg_pull(XchgRow* rows, int world, unsigned long long step_plus1, int d, int D, int g_lo, int g_hi,
                                           long long& dc, long long& dm) {
-    const unsigned long long tag = xchg_tag(step_plus1);
-    const long long t0 = clock64();
-    for (int g = 0; g < world; ++g) {
-        unsigned long long* pc = &rows[g].ll[2 * d];
-        unsigned long long* pm = &rows[g].ll[2 * (D + d)];
-        unsigned long long c0, c1, m0, m1;
-        for (;;) {
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(pc) : "memory");
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(m0), "=l"(m1) : "l"(pm) : "memory");
-            if ((c0 >> 32) == tag && (c1 >> 32) == tag && (m0 >> 32) == tag && (m1 >> 32) == tag) break;
-            if (clock64() - t0 > 4000000000ll) return false;
-            __nanosleep(40);
-        }
-        if (g >= g_lo && g < g_hi) {
-            dc += static_cast<long long>((c0 & 0xffffffffull) | (c1 << 32));
-            dm += static_cast<long long>((m0 & 0xffffffffull) | (m1 << 32));
-        }
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pc), "l"(0ull) : "memory");
-        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(pm), "l"(0ull) : "memory");
-    }
-    return true;
+    return xchg_pull_word(rows, world, step_plus1, d, g_lo, g_hi, dc) && xchg_pull_word(rows, world, step_plus1, D + d, g_lo, g_hi, dm);
 }
 
 // Where a CTA's epilogue goes: the launch's (or, in a multi-batch launch, the batch's) slot of

@@ -392,3 +392,95 @@ def test_world2_prefix_commit_rank_major(oracle_c, egpu):
     assert cuts_in_rank1 >= 3, "the cases must put some cuts inside rank 1's shard"
     for res in (r0, r1):
         assert np.array_equal(res[2], cur_c) and np.array_equal(res[3], cur_m)
+
+
+# ------------------------------------------------------------------ more than four ranks (second pull group)
+def _rank_main_n(rank, world, conn, steps, R, fused):
+    """One of `world` processes on GPU 0; the parent relays the IPC handles.  fused = False: one sharded scan
+    + one apply launch per step; True: the steps as one multi-batch launch with EGPU_F_APPLY (the word
+    finishers of the scan pull the peers' words themselves)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import elastic_gpu_agent_b200 as e
+    torch.cuda.set_device(0)
+    w = e.synth.workload("cfg3")
+    a = e.BestFitAllocator(0)
+    a.set_table(w["free_core"], w["free_mem"])
+    conn.send(a.peer_export())
+    a.peer_attach(rank, world, conn.recv())
+    conn.send("attached")
+    assert conn.recv() == "go"
+    s = torch.cuda.current_stream().cuda_stream
+    D = 8
+    keep, tup = [], []
+    for step in range(steps):
+        rc, rm = e.synth.requests(3, 90 + step, R, first_row=rank * R)
+        c, m = torch.from_numpy(rc).cuda(), torch.from_numpy(rm).cuda()
+        idx = torch.empty(R, dtype=torch.int32, device="cuda")
+        dl = torch.zeros(2 * D, dtype=torch.int64, device="cuda")
+        tab = torch.zeros(3 * D, dtype=torch.int32, device="cuda")
+        keep.append((c, m, idx, dl, tab))
+        tup.append((c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), tab.data_ptr()))
+    torch.cuda.synchronize()
+    if fused:
+        a.bestfit_batches_shard_dev(a.make_batches(tup), 0, s, inputs_ready=True, apply=True)
+    else:
+        for step, (c, m, idx, dl, tab) in enumerate(keep):
+            a.bestfit_shard_dev(c.data_ptr(), m.data_ptr(), R, idx.data_ptr(), dl.data_ptr(), step, s)
+            a.apply_peers_dev(step, tab.data_ptr(), False, s)
+    torch.cuda.synchronize()
+    conn.send((rank, [(idx.cpu().numpy(), dl.cpu().numpy(), tab.cpu().numpy()) for c, m, idx, dl, tab in keep], a.peer_last_timeout))
+    assert conn.recv() == "done"
+    a.peer_detach()
+    a.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+def test_world6_six_processes_one_gpu(fused, oracle_c, egpu):
+    """Six ranks: the waits collect the peers' words four ranks at a time, so ranks 4 and 5 come from the
+    second group - in apply_peers_kernel and in the scan's own epilogue (EGPU_F_APPLY)."""
+    import torch.multiprocessing as mp
+    from elastic_gpu_agent_b200 import sharding
+    ctx = mp.get_context("spawn")
+    world, steps, R, D = 6, 3, 4_001, 8
+    conns, procs = [], []
+    for rank in range(world):
+        parent, child = ctx.Pipe()
+        p = ctx.Process(target=_rank_main_n, args=(rank, world, child, steps, R, fused))
+        p.start()
+        conns.append(parent)
+        procs.append(p)
+    try:
+        assert all(c.poll(240) for c in conns), "ranks did not come up"
+        handles = [c.recv() for c in conns]
+        for c in conns:
+            c.send(handles)
+        assert all(c.poll(120) and c.recv() == "attached" for c in conns)
+        for c in conns:
+            c.send("go")
+        assert all(c.poll(240) for c in conns), "ranks did not finish"
+        res = sorted((c.recv() for c in conns), key=lambda r: r[0])
+        for c in conns:
+            c.send("done")
+        for p in procs:
+            p.join(60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(r[2] == 0 for r in res), "a wait for a peer timed out"
+    w = egpu.synth.workload("cfg3")
+    for step in range(steps):
+        tot = np.zeros(2 * D, dtype=np.int64)
+        for rank in range(world):
+            rc, rm = egpu.synth.requests(3, 90 + step, R, first_row=rank * R)
+            o_idx, o_dc, o_dm, _ = oracle_c.snapshot(w["free_core"], w["free_mem"], rc, rm)
+            idx, dl, _ = res[rank][1][step]
+            assert np.array_equal(idx, o_idx), f"indices rank {rank} step {step}"
+            assert np.array_equal(dl, np.concatenate([o_dc, o_dm]))
+            tot += np.concatenate([o_dc, o_dm])
+        etab = sharding.combine_demands(w["free_core"], w["free_mem"], tot[None, :])
+        for rank in range(world):
+            assert np.array_equal(res[rank][1][step][2], etab), f"table' rank {rank} step {step}"
