@@ -237,8 +237,8 @@ class BestFitAllocator:
 
     def bestfit_batches_shard_dev(self, batches, first_step: int, stream: int | None = None, inputs_ready: bool = False,
                                   apply: bool = False):
-        """K sharded steps in one launch: batch k = exchange step first_step + k.  apply: the last CTA of every
-        batch also applies that step (EGPU_F_APPLY) - table' lands in the batch's d_table_out, no apply call."""
+        """K sharded steps in one launch: batch k = exchange step first_step + k.  apply: the CTAs that complete a
+        batch's sums also apply that step (EGPU_F_APPLY) - table' lands in the batch's d_table_out, no apply call."""
         arr = batches if isinstance(batches, C.Array) else self.make_batches(batches)
         rc = self._lib.egpu_bestfit_batches_shard_dev(self._h, arr, len(arr),
                                                       (L.F_INPUTS_READY if inputs_ready else 0) | (L.F_APPLY if apply else 0),

@@ -41,7 +41,7 @@ constexpr uint32_t kNoCand = 32u;  // "no feasible row" among 32 positions
 constexpr uint32_t kPadWord = kGuardC;
 
 // flags of the snapshot kernels
-constexpr int kFlagFinalize = 1;  // last CTA publishes delta / table'
+constexpr int kFlagFinalize = 1;  // the batch's demand sums are complete after this launch: publish delta / table'
 constexpr int kFlagCommit = 2;    // table' replaces the table
 constexpr int kFlagLateWait = 4;  // programmatic dependent launch: this launch shares nothing
                                   // with the launches in flight before it, so it triggers its
@@ -52,7 +52,7 @@ constexpr int kFlagBoundary = 16;     // with kFlagLateWait: group boundary of a
                                       // alongside the predecessors, but wait for them BEFORE the epilogue
                                       // and only then trigger: everything older is complete when the next
                                       // group starts, which bounds the launches in flight
-constexpr int kFlagApplyNow = 32;     // multi-batch sharded launches: the last CTA of a batch also applies that batch's exchange step
+constexpr int kFlagApplyNow = 32;     // multi-batch sharded launches: the CTAs that finish a batch's sums also apply that batch's exchange step
 constexpr int kFlagEarlyTrigger = 8;  // griddepcontrol.launch_dependents before the scan: only on
                                       // streams the caller declared pipelined (EGPU_F_INPUTS_READY)
 

@@ -1,7 +1,7 @@
 // egpu_scan.cuh — snapshot-mode kernels of the best-fit path (sm_100a): the register scan
 // (bestfit_sorted_kernel and its multi-batch form), its packed-format twin, the literal grid
 // scan, the lookup-table scan for large D (single- and multi-batch) with its table builder, the
-// shared epilogue (demand sums, arrival ticket, last-CTA publication, fused peer push / apply),
+// shared epilogue (demand sums with the arrival count inside them, publication by each word's finisher, fused peer push / apply),
 // the exchange-word helpers, the apply kernels, the start gate, and the prefix-commit and
 // rounds kernels.  Included by egpu_alloc.cu only; see DESIGN.md §4, §5.
 #pragma once
@@ -203,7 +203,7 @@ __device__ __forceinline__ EpiCtl epi_from_word(DevState* st, unsigned long long
 // Second half of every snapshot epilogue.  `wacc` holds per-warp demand sums in shared
 // memory: core sum of device d of warp w at wacc[w * wstride + core_off + d], mem sum at
 // [... + mem_off + d].  Called by all threads after a __syncthreads().  Publishes the CTA's
-// sums with one red.global.add.u64 per device, takes an arrival ticket, and the last CTA
+// sums; plain snapshots finish word by word (below), every other mode adds with red.global.add.u64, takes an arrival ticket, and the last CTA
 // writes delta / table', optionally commits (and re-sorts) the table and resets the slot.
 template <int WARPS>
 __device__ __forceinline__ void epilogue_publish(const unsigned long long* wacc, int wstride, int core_off, int mem_off,
@@ -515,9 +515,9 @@ __device__ __forceinline__ void multi_cta_to_tile(int tiles_extra, int& batch, i
 
 // Multi-batch launch (egpu_bestfit_batches_dev): K independent batches, all scored against the
 // same table, in ONE grid.  CTA (b, t) = tile t of batch b; every batch has its own epilogue
-// slot, so its last CTA publishes that batch's demand sums / table' (and pushes its exchange
-// step) as soon as that batch is done.  One launch latency, one ramp and one tail for K batches
-// instead of K: what the per-launch fixed cost (first DRAM touch, atomics, fence, ticket) was
+// slot, so that batch's demand sums / table' are published (and its exchange step pushed) by its
+// own CTAs as soon as that batch is done.  One launch latency, one ramp and one tail for K batches
+// instead of K: what the per-launch fixed cost (first DRAM touch, the epilogue's atomics) was
 // eating at R = 1 M, and the launch floor at R = 1 k .. 100 k.
 template <int DT, int THREADS>
 __global__ void __launch_bounds__(THREADS)

@@ -105,9 +105,9 @@ extern "C" {
                                     Single GPU; not with EGPU_VARIANT_GRID.  In egpu_bestfit_batch
                                     pass it in `commit` (EGPU_F_COMMIT | EGPU_F_PREFIX_COMMIT). */
 
-#define EGPU_F_APPLY         8   /* egpu_bestfit_batches_shard_dev only: the last CTA of every batch, having pushed the
-                                    batch's demand vector, also waits for the peers' vectors of that exchange step and
-                                    writes table' (= table - sum over ranks) to the batch's d_table_out: no apply call,
+#define EGPU_F_APPLY         8   /* egpu_bestfit_batches_shard_dev only: the CTAs that complete a batch's sums, having pushed the
+                                    batch's demand vector, also wait for the peers' vectors of that exchange step and
+                                    write table' (= table - sum over ranks) to the batch's d_table_out: no apply call,
                                     no second stream.  Never commits.  Every rank must issue the same launch; start the
                                     ranks together (egpu_peer_gate_dev) or the wait is as long as their skew. */
 
