@@ -98,6 +98,7 @@ struct egpu_ctx {
     int threads8 = 256;               // CTA size of the D <= 8 register scan (EGPU_THREADS8 = 128 | 256 | 512)
     int replay_variant = 2;           // 2 = two-warp kernel where it applies (EGPU_REPLAY_VARIANT=1: round 1's one-warp kernels)
     bool replay2_configured = false;
+    bool sort_sets_configured = false;  // sort_sets_smem_kernel may use 128 KB of dynamic shared memory
     bool replay_general = false;      // EGPU_REPLAY_GENERAL=1: lane = device kernel even for D <= 8 (tests)
     // grow-only device arena for multi-kernel host-buffer pipelines (egpu_devhash.cu)
     void* arena = nullptr;

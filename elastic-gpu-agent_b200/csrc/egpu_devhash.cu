@@ -13,6 +13,7 @@
 //             one thread per ID writes the characters and the ':' separator
 //   sha256    one thread per set walks its message in 64-byte blocks (the chain is serial)
 //   locate    candidate set == request set iff same size and all sorted keys equal
+#include <algorithm>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
@@ -82,7 +83,44 @@ __global__ void pack_ids_kernel(const char* __restrict__ flat, long long flat_by
     len1[i] = static_cast<uint32_t>(ok ? l : 0) + 1u;  // + ':' (the last one of a set is dropped later)
 }
 
-// ---- LSD radix sort, 4-bit digit, stable -----------------------------------------
+// ---- sort inside the sets, in shared memory -------------------------------------------
+// The IDs of a set are contiguous in the input (set_off), so "(set, key) order" is every set's own
+// range in key order.  When the largest set fits shared memory (<= 16 384 keys = 128 KB; a node-scale
+// container has 4 K .. 16 K IDs) one CTA per set runs a bitonic network over its range, padded to a
+// power of two with all-ones keys (no packed ID has a 0xF nibble): 105 barrier-separated steps at
+// 16 K, ~20 us for the whole batch, against ten global radix passes of three kernels (~0.55 ms for
+// 934 k IDs).  Equal keys are equal IDs, so the network's instability is invisible.
+constexpr int kSortSmemMaxKeys = 16384;
+__global__ void __launch_bounds__(1024)
+sort_sets_smem_kernel(unsigned long long* __restrict__ key, const long long* __restrict__ set_off) {
+    extern __shared__ unsigned long long sk[];
+    const long long b = set_off[blockIdx.x];
+    const int n = static_cast<int>(set_off[blockIdx.x + 1] - b);
+    if (n <= 1) return;
+    int np = 2;
+    while (np < n) np <<= 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < np; i += nt) sk[i] = i < n ? key[b + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (np >> 1); t += nt) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t with a 0 inserted at bit log2(j)
+                const int p = i | j;
+                const unsigned long long a = sk[i], c = sk[p];
+                const bool ascending = (i & k) == 0;
+                if ((a > c) == ascending) {
+                    sk[i] = c;
+                    sk[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += nt) key[b + i] = sk[i];
+}
+
+// ---- LSD radix sort, 4-bit digit, stable (sets too large for shared memory) ------------
 // digit source: shift < 64 -> key nibble, else set-index nibble (shift - 64)
 __device__ __forceinline__ uint32_t digit_of(unsigned long long k, uint32_t s, int shift) {
     return shift < 64 ? static_cast<uint32_t>(k >> shift) & 15u : (s >> (shift - 64)) & 15u;
@@ -575,8 +613,12 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
     if (n_sets > (1ll << 24) || n_ids > (1ll << 31) - 1) return EGPU_ERR_INVALID;
     const int64_t flat_bytes = id_offsets[n_ids];
     if (flat_bytes < 0 || (flat_bytes > 0 && !ids_flat)) return EGPU_ERR_INVALID;
-    for (int64_t q = 0; q < n_sets; ++q)
+    int64_t max_set = 0;
+    for (int64_t q = 0; q < n_sets; ++q) {
         if (set_offsets[q + 1] < set_offsets[q]) return EGPU_ERR_INVALID;
+        max_set = std::max<int64_t>(max_set, set_offsets[q + 1] - set_offsets[q]);
+    }
+    const bool smem_sort = max_set <= kSortSmemMaxKeys && n_sets <= 65536;
     // the n_ids-long arrays are not walked here: lengths, bounds, set membership and the longest ID
     // come from pack_ids_kernel (a pageable 1 M-ID batch spent more host time on that than the GPU on the sort)
     const size_t n = static_cast<size_t>(n_ids);
@@ -607,6 +649,21 @@ int run_hash(egpu_ctx* ctx, HashRun& r, const char* ids_flat, const int64_t* id_
         pack_ids_kernel<<<nb256, 256, 0, s>>>(r.flat.as<char>(), flat_bytes, r.id_off.as<long long>(), n_ids,
                                               r.set_off.as<long long>(), n_sets, ka, sa, r.len1.as<uint32_t>(), r.err.as<HashErr>());
         ctx->launches += 1;
+    }
+    if (n && smem_sort) {
+        int np = 2;
+        while (np < max_set) np <<= 1;
+        const size_t smem = sizeof(unsigned long long) * static_cast<size_t>(np);
+        if (!ctx->sort_sets_configured) {
+            EGPU_CUDA(ctx, cudaFuncSetAttribute(sort_sets_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(sizeof(unsigned long long) * kSortSmemMaxKeys)));
+            ctx->sort_sets_configured = true;
+        }
+        const int threads = np / 2 >= 1024 ? 1024 : (np / 2 < 32 ? 32 : np / 2);
+        sort_sets_smem_kernel<<<static_cast<unsigned>(n_sets), threads, smem, s>>>(ka, r.set_off.as<long long>());
+        ctx->launches += 1;
+        EGPU_CUDA(ctx, cudaGetLastError());
+    } else if (n) {
         HashErr first{0, 0};
         EGPU_CUDA(ctx, cudaMemcpyAsync(&first, r.err.p, sizeof first, cudaMemcpyDeviceToHost, s));
         EGPU_CUDA(ctx, cudaStreamSynchronize(s));

@@ -163,3 +163,21 @@ def test_cuda_empty_sets_between_full_ones_and_bad_offsets(alloc, egpu):
             devhash.device_hashes_flat(alloc, flat, off, set_off)
         assert ei.value.code in (-7, -1), bad
     assert devhash.device_hashes_flat(alloc, flat, id_off, set_off) == [hashlib.sha256(b"0-01:0-02:0-03").hexdigest()[:8]]
+
+
+@pytest.mark.gpu
+def test_cuda_sets_larger_than_shared_memory_take_the_radix_path(alloc, egpu):
+    """Sets of up to 16 384 IDs are sorted by one CTA each in shared memory; a batch with a larger set goes
+    through the global (set, key) radix sort.  Both must give the reference's hashes, and Locate must agree."""
+    import hashlib
+    import random
+    from elastic_gpu_agent_b200 import devhash
+    rng = random.Random(17)
+    big = ["%d-%02d" % (rng.randrange(8), j) for j in rng.sample(range(183359), 20_000)]
+    small = [["5-07", "5-03", "12-00"], [], ["0-%02d" % j for j in rng.sample(range(9000), 4097)], ["3-100000"]]
+    for sets in (small, [big] + small, small + [big[:16_385]], small + [big[:16_384]]):
+        exp = [hashlib.sha256(":".join(sorted(x)).encode()).hexdigest()[:8] for x in sets]
+        assert devhash.device_hashes(alloc, sets) == exp
+        req = list(sets[-1])
+        rng.shuffle(req)
+        assert devhash.locate(alloc, req, sets) == len(sets) - 1
