@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/egpu_plugin.h"
@@ -64,6 +65,8 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
     std::vector<int64_t> unit_of(static_cast<size_t>(n_available));
     int32_t D = 0;
     for (int64_t i = 0; i < n_available; ++i) {
+        // the strings are wherever the caller's runtime put them: one cache miss each unless asked for early
+        if (i + 16 < n_available) __builtin_prefetch(available_ids[i + 16]);
         const int rc = egpu_device_id_parse(available_ids[i], &gpu_of[i], &unit_of[i]);
         if (rc != EGPU_OK) return rc;
         if (gpu_of[i] >= EGPU_MAX_DEVICES) return EGPU_ERR_INVALID;
@@ -140,23 +143,24 @@ int egpu_preferred_allocation(egpu_ctx* ctx, const char* const* available_ids, i
         }
     }
     for (int32_t g : chosen) {
-        std::vector<int32_t> cand;
+        // candidates as (unit, position) pairs: their natural order is the selection rule (lowest unit first,
+        // the earlier position among equal units) and the comparisons stay inside one contiguous array
+        std::vector<std::pair<int64_t, int32_t>> cand;
         for (int64_t i = 0; i < n_available; ++i)
-            if (gpu_of[i] == g && !taken[i]) cand.push_back(static_cast<int32_t>(i));
+            if (gpu_of[i] == g && !taken[i]) cand.emplace_back(unit_of[i], static_cast<int32_t>(i));
         // a single-GPU request takes what it still needs; a whole card gives all 100 of its units
         const int32_t want = whole_cards ? EGPU_CORE_MAX : allocation_size;
         int32_t have = 0;
         for (int32_t i = 0; i < n_out; ++i) have += gpu_of[out_positions[i]] == g;
         // only the `want - have` lowest unit numbers are needed: select them, then order them (a gpu-memory
         // plugin on a B200 offers 183 359 IDs per GPU: sorting them all was half of the call)
-        const auto by_unit = [&](int32_t a, int32_t b) { return unit_of[a] != unit_of[b] ? unit_of[a] < unit_of[b] : a < b; };
         const size_t need = static_cast<size_t>(want > have ? want - have : 0);
         if (need < cand.size()) {
-            std::nth_element(cand.begin(), cand.begin() + static_cast<std::ptrdiff_t>(need), cand.end(), by_unit);
+            std::nth_element(cand.begin(), cand.begin() + static_cast<std::ptrdiff_t>(need), cand.end());
             cand.resize(need);
         }
-        std::sort(cand.begin(), cand.end(), by_unit);
-        for (size_t k = 0; k < cand.size() && have < want && n_out < allocation_size; ++k, ++have) out_positions[n_out++] = cand[k];
+        std::sort(cand.begin(), cand.end());
+        for (size_t k = 0; k < cand.size() && have < want && n_out < allocation_size; ++k, ++have) out_positions[n_out++] = cand[k].second;
     }
     return n_out == allocation_size ? EGPU_OK : EGPU_ERR_UNSAT;
 }
